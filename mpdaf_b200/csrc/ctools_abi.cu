@@ -1,0 +1,690 @@
+// C ABI of the B200 `_ctools` replacement (see include/mpdaf_b200.h).
+//
+// Host side of the hot path: argument checking, kernel selection, the slab
+// pipeline for host-resident stacks and for FITS files, counter read-back.
+// Everything computational happens in the kernels of combine_kernels.cuh; there
+// is no CPU fallback -- a missing device is an error.
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mpdaf_b200.h"
+#include "combine_kernels.cuh"
+#include "fits_reader.h"
+#include "synth_core.h"
+
+namespace {
+
+using namespace mb;
+
+thread_local std::string g_error;
+std::mutex g_call_mutex;              // one merging call at a time (ctools.py contract)
+double g_last_kernel_ms = 0.0;
+int g_last_launches = 0;
+std::string g_last_kernel = "none";
+
+int fail(int code, const std::string& msg)
+{
+    g_error = msg;
+    std::fprintf(stderr, "mpdaf_b200: %s\n", msg.c_str());
+    return code;
+}
+
+#define MB_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(MPDAF_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// per-device state
+// ---------------------------------------------------------------------------
+struct DeviceState {
+    bool ready = false;
+    int sm_count = 0;
+    unsigned long long* counters = nullptr;  // [2][kGenericMax]: valid, select
+    StackTable* table = nullptr;             // device copy for the generic kernels
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+DeviceState g_dev[16];
+
+int device_ready(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0)
+        return fail(MPDAF_B200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= count || device >= 16) return fail(MPDAF_B200_ERR_ARG, "bad device index");
+    MB_CUDA(cudaSetDevice(device));
+    DeviceState& d = g_dev[device];
+    if (d.ready) return MPDAF_B200_OK;
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(MPDAF_B200_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
+    d.sm_count = prop.multiProcessorCount;
+    MB_CUDA(cudaMalloc(&d.counters, 2 * kGenericMax * sizeof(unsigned long long)));
+    MB_CUDA(cudaMalloc(&d.table, sizeof(StackTable)));
+    MB_CUDA(cudaEventCreate(&d.ev0));
+    MB_CUDA(cudaEventCreate(&d.ev1));
+    d.ready = true;
+    return MPDAF_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel selection
+// ---------------------------------------------------------------------------
+struct Job {
+    int nfiles = 0;
+    int elem = MPDAF_B200_F32;
+    bool median = false;
+    const void* const* data = nullptr;  // host table of DEVICE pointers
+    const void* const* var = nullptr;
+    const double* scale = nullptr;       // host, may be null
+    const double* offset = nullptr;
+    StackTable* table_dev = nullptr;     // device scratch for the generic kernels' stack table
+    ClipArgs a{};
+};
+
+int bucket_of(int nfiles)
+{
+    const int sizes[] = {4, 8, 12, 16, 24, 32, 48, 64};
+    for (int s : sizes)
+        if (nfiles <= s) return s;
+    return 0;
+}
+
+template <typename Kernel, typename... Args>
+int launch_persistent(Kernel kernel, int device, long long nvox, cudaStream_t stream, Args... args)
+{
+    int per_sm = 0;
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long want = (nvox + kThreads - 1) / kThreads;
+    const long long cap = (long long)g_dev[device].sm_count * per_sm;
+    const int grid = (int)std::max(1LL, std::min(want, cap));
+    kernel<<<grid, kThreads, 0, stream>>>(args...);
+    MB_CUDA(cudaGetLastError());
+    g_last_launches++;
+    return MPDAF_B200_OK;
+}
+
+template <int NB>
+void fill_stack(StackArgs<NB>& s, const Job& j)
+{
+    for (int i = 0; i < NB; i++) {
+        const bool in = i < j.nfiles;
+        s.data[i] = in ? j.data[i] : nullptr;
+        s.var[i] = (in && j.var) ? j.var[i] : nullptr;
+        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
+        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
+        s.scale2[i] = s.scale[i] * s.scale[i];
+    }
+}
+
+template <int NB>
+int launch_reg(const Job& j, bool unit, int device, cudaStream_t stream)
+{
+    StackArgs<NB> s;
+    fill_stack(s, j);
+    char name[64];
+    if (j.median) {
+        std::snprintf(name, sizeof name, "median_reg<%d>", NB);
+        g_last_kernel = name;
+        return launch_persistent(median_reg_kernel<NB>, device, j.a.nvox, stream, s, j.a);
+    }
+    std::snprintf(name, sizeof name, "sigclip_reg<%d,%s>", NB, unit ? "unit" : "scaled");
+    g_last_kernel = name;
+    if (unit) return launch_persistent(sigclip_reg_kernel<NB, true>, device, j.a.nvox, stream, s, j.a);
+    return launch_persistent(sigclip_reg_kernel<NB, false>, device, j.a.nvox, stream, s, j.a);
+}
+
+template <int MAXN, typename ElemT>
+int launch_generic(const Job& j, int device, cudaStream_t stream)
+{
+    // the table upload is ordered on `stream`; a pinned bounce buffer is not needed
+    // because cudaMemcpyAsync from pageable memory returns after staging the source
+    static StackTable host;  // guarded by g_call_mutex
+    std::memset(&host, 0, sizeof host);
+    for (int i = 0; i < j.nfiles; i++) {
+        host.data[i] = j.data[i];
+        host.var[i] = j.var ? j.var[i] : nullptr;
+        host.scale[i] = j.scale ? j.scale[i] : 1.0;
+        host.offset[i] = j.offset ? j.offset[i] : 0.0;
+        host.scale2[i] = host.scale[i] * host.scale[i];
+    }
+    MB_CUDA(cudaMemcpyAsync(j.table_dev, &host, sizeof host, cudaMemcpyHostToDevice, stream));
+    char name[64];
+    std::snprintf(name, sizeof name, "%s_generic<%d,f%d>", j.median ? "median" : "sigclip", MAXN,
+                  (int)sizeof(ElemT) * 8);
+    g_last_kernel = name;
+    if (j.median)
+        return launch_persistent(median_generic_kernel<MAXN, ElemT>, device, j.a.nvox, stream,
+                                 (const StackTable*)j.table_dev, j.a);
+    return launch_persistent(sigclip_generic_kernel<MAXN, ElemT>, device, j.a.nvox, stream,
+                             (const StackTable*)j.table_dev, j.a);
+}
+
+// Enqueue the combination of one device-resident stack (or slab) on `stream`.
+int enqueue_combine(const Job& j, int device, cudaStream_t stream)
+{
+    bool unit = true;
+    for (int i = 0; i < j.nfiles; i++) {
+        if (j.scale && j.scale[i] != 1.0) unit = false;
+        if (j.offset && j.offset[i] != 0.0) unit = false;
+    }
+    const int nb = bucket_of(j.nfiles);
+    const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32 && (j.median || !j.a.mad);
+    if (reg_ok) {
+        switch (nb) {
+            case 4: return launch_reg<4>(j, unit, device, stream);
+            case 8: return launch_reg<8>(j, unit, device, stream);
+            case 12: return launch_reg<12>(j, unit, device, stream);
+            case 16: return launch_reg<16>(j, unit, device, stream);
+            case 24: return launch_reg<24>(j, unit, device, stream);
+            case 32: return launch_reg<32>(j, unit, device, stream);
+            case 48: return launch_reg<48>(j, unit, device, stream);
+            case 64: return launch_reg<64>(j, unit, device, stream);
+        }
+    }
+    if (j.nfiles <= 128) {
+        if (j.elem == MPDAF_B200_F32) return launch_generic<128, float>(j, device, stream);
+        return launch_generic<128, double>(j, device, stream);
+    }
+    if (j.elem == MPDAF_B200_F32) return launch_generic<kGenericMax, float>(j, device, stream);
+    return launch_generic<kGenericMax, double>(j, device, stream);
+}
+
+int check_common(int nfiles, const void* const* data, int elem_type, long long nvox, int location)
+{
+    if (nfiles < 1 || nfiles > MPDAF_B200_MAX_FILES) return fail(MPDAF_B200_ERR_ARG, "nfiles must be in 1..500");
+    if (elem_type != MPDAF_B200_F32 && elem_type != MPDAF_B200_F64) return fail(MPDAF_B200_ERR_ARG, "elem_type must be 4 or 8");
+    if (nvox < 0 || data == nullptr) return fail(MPDAF_B200_ERR_ARG, "bad stack description");
+    if (location != MPDAF_B200_HOST && location != MPDAF_B200_DEVICE) return fail(MPDAF_B200_ERR_ARG, "bad location");
+    for (int i = 0; i < nfiles; i++)
+        if (data[i] == nullptr && nvox > 0) return fail(MPDAF_B200_ERR_ARG, "null exposure pointer");
+    return MPDAF_B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// slab pipeline: host-resident stacks and FITS files
+// ---------------------------------------------------------------------------
+struct Slot {
+    cudaStream_t stream = nullptr;
+    char* d_in = nullptr;      // [planes][chunk] samples (data planes then var planes)
+    double* d_out = nullptr;
+    double* d_var = nullptr;
+    int* d_exp = nullptr;
+    char* h_in = nullptr;      // pinned staging for file reads
+    StackTable* d_table = nullptr;
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    bool timed = false;
+};
+
+struct SlabSource {
+    // exactly one of the two is used
+    const void* const* host_data = nullptr;
+    const void* const* host_var = nullptr;
+    std::vector<mbfits::ImageHdu>* fits_data = nullptr;
+    std::vector<mbfits::ImageHdu>* fits_var = nullptr;
+};
+
+void release_slots(std::vector<Slot>& slots)
+{
+    for (Slot& s : slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_in);
+        cudaFree(s.d_out);
+        cudaFree(s.d_var);
+        cudaFree(s.d_exp);
+        cudaFree(s.d_table);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.k0) cudaEventDestroy(s.k0);
+        if (s.k1) cudaEventDestroy(s.k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    slots.clear();
+}
+
+long long env_ll(const char* name, long long dflt)
+{
+    const char* v = std::getenv(name);
+    return v ? std::atoll(v) : dflt;
+}
+
+// Runs the whole stack through `device` in chunks of consecutive voxels.
+int run_slabs(const SlabSource& src, Job job, int device, double* out, double* outvar, int* expmap)
+{
+    const int nfiles = job.nfiles;
+    const bool need_var = !job.median && job.a.typ_var == 0;
+    const int planes = nfiles * (need_var ? 2 : 1);
+    const int esz = job.elem;
+    const long long nvox = job.a.nvox;
+    const bool from_files = src.fits_data != nullptr;
+
+    // chunk: bounded staging (default 768 MiB of samples per slot), multiple of 1024 voxels
+    const long long budget = env_ll("MPDAF_B200_SLAB_BYTES", 768LL << 20);
+    long long chunk = budget / ((long long)planes * esz);
+    chunk = std::max(1024LL, chunk / 1024 * 1024);
+    chunk = std::min(chunk, (nvox + 1023) / 1024 * 1024);
+    if (chunk < 1) chunk = 1024;
+    const int nslots = (int)std::min<long long>(3, (nvox + chunk - 1) / chunk);
+
+    std::vector<Slot> slots(std::max(nslots, 1));
+    for (Slot& s : slots) {
+        MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaMalloc(&s.d_in, (size_t)planes * chunk * esz));
+        MB_CUDA(cudaMalloc(&s.d_out, (size_t)chunk * sizeof(double)));
+        if (!job.median) MB_CUDA(cudaMalloc(&s.d_var, (size_t)chunk * sizeof(double)));
+        MB_CUDA(cudaMalloc(&s.d_exp, (size_t)chunk * sizeof(int)));
+        MB_CUDA(cudaMalloc(&s.d_table, sizeof(StackTable)));
+        if (from_files) MB_CUDA(cudaMallocHost(&s.h_in, (size_t)planes * chunk * esz));
+        MB_CUDA(cudaEventCreate(&s.k0));
+        MB_CUDA(cudaEventCreate(&s.k1));
+    }
+
+    int rc = MPDAF_B200_OK;
+    double kernel_ms = 0.0;
+    std::vector<const void*> dptr(planes);
+    long long c = 0;
+    for (long long v0 = 0; v0 < nvox && rc == MPDAF_B200_OK; v0 += chunk, c++) {
+        Slot& s = slots[c % slots.size()];
+        const long long cnt = std::min(chunk, nvox - v0);
+        // the slot's previous chunk must have left the device (and its pinned staging)
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess) { rc = fail(MPDAF_B200_ERR_CUDA, "slab stream failed"); break; }
+        if (s.timed) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.k0, s.k1);
+            kernel_ms += ms;
+            s.timed = false;
+        }
+        for (int p = 0; p < planes; p++) dptr[p] = s.d_in + (size_t)p * chunk * esz;
+
+        if (from_files) {
+            // parallel pread of every exposure's byte range into pinned staging
+            std::atomic<int> next{0}, bad{0};
+            std::string first_err;
+            std::mutex err_mutex;
+            auto worker = [&]() {
+                for (;;) {
+                    const int p = next.fetch_add(1);
+                    if (p >= planes) return;
+                    const mbfits::ImageHdu& h = p < nfiles ? (*src.fits_data)[p] : (*src.fits_var)[p - nfiles];
+                    std::string err;
+                    if (mbfits::read_raw(h, v0, cnt, s.h_in + (size_t)p * chunk * esz, &err) != MPDAF_B200_OK) {
+                        std::lock_guard<std::mutex> lk(err_mutex);
+                        if (!bad.exchange(1)) first_err = err;
+                    }
+                }
+            };
+            const int nthreads = (int)std::min<long long>(planes, std::max(1LL, env_ll("MPDAF_B200_IO_THREADS", 8)));
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
+            for (auto& t : pool) t.join();
+            if (bad.load()) { rc = fail(MPDAF_B200_ERR_IO, first_err); break; }
+            if (cudaMemcpyAsync(s.d_in, s.h_in, (size_t)planes * chunk * esz, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) {
+                rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a FITS slab failed");
+                break;
+            }
+            const long long words = (long long)planes * chunk * (esz / 4);
+            // FITS is big-endian: swap 32-bit words (for f64 the word pair is swapped by the 64-bit variant)
+            if (esz == 4) {
+                bswap32_kernel<<<1024, 256, 0, s.stream>>>((uint32_t*)s.d_in, words);
+            } else {
+                bswap64_kernel<<<1024, 256, 0, s.stream>>>((unsigned long long*)s.d_in, (long long)planes * chunk);
+            }
+            g_last_launches++;
+        } else {
+            for (int p = 0; p < planes && rc == MPDAF_B200_OK; p++) {
+                const char* base = (const char*)(p < nfiles ? src.host_data[p] : src.host_var[p - nfiles]);
+                if (cudaMemcpyAsync(s.d_in + (size_t)p * chunk * esz, base + (size_t)v0 * esz, (size_t)cnt * esz,
+                                    cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+                    rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a host slab failed");
+            }
+            if (rc != MPDAF_B200_OK) break;
+        }
+
+        Job j = job;
+        j.data = dptr.data();
+        j.var = need_var ? dptr.data() + nfiles : nullptr;
+        j.table_dev = s.d_table;
+        j.a.nvox = cnt;
+        j.a.out = s.d_out;
+        j.a.outvar = s.d_var;
+        j.a.expmap = s.d_exp;
+        cudaEventRecord(s.k0, s.stream);
+        rc = enqueue_combine(j, device, s.stream);
+        if (rc != MPDAF_B200_OK) break;
+        cudaEventRecord(s.k1, s.stream);
+        s.timed = true;
+        bool ok = cudaMemcpyAsync(out + v0, s.d_out, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+        if (!job.median)
+            ok = ok && cudaMemcpyAsync(outvar + v0, s.d_var, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(expmap + v0, s.d_exp, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+        if (!ok) rc = fail(MPDAF_B200_ERR_CUDA, "D2H of a result slab failed");
+    }
+    for (Slot& s : slots) {
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc == MPDAF_B200_OK)
+            rc = fail(MPDAF_B200_ERR_CUDA, std::string("slab pipeline: ") + cudaGetErrorString(cudaGetLastError()));
+        if (s.timed) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.k0, s.k1);
+            kernel_ms += ms;
+        }
+    }
+    g_last_kernel_ms = kernel_ms;
+    release_slots(slots);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// shared driver for all merging entry points
+// ---------------------------------------------------------------------------
+struct CounterSink {
+    int* valid32 = nullptr;
+    int* select32 = nullptr;
+    long long* valid64 = nullptr;
+    long long* select64 = nullptr;
+};
+
+int run_job(Job job, const SlabSource* slab_src, int location, int device, double* out, double* outvar,
+            int* expmap, CounterSink sink, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    g_last_launches = 0;
+    g_last_kernel_ms = 0.0;
+    int rc = device_ready(device);
+    if (rc != MPDAF_B200_OK) return rc;
+    DeviceState& d = g_dev[device];
+    const int nfiles = job.nfiles;
+    job.a.valid_cnt = d.counters;
+    job.a.select_cnt = job.median ? nullptr : d.counters + kGenericMax;
+
+    cudaStream_t cstream = (location == MPDAF_B200_DEVICE) ? stream : nullptr;
+    MB_CUDA(cudaMemsetAsync(d.counters, 0, 2 * kGenericMax * sizeof(unsigned long long), cstream));
+    if (location == MPDAF_B200_DEVICE) {
+        job.table_dev = d.table;
+        job.a.out = out;
+        job.a.outvar = outvar;
+        job.a.expmap = expmap;
+        if (job.a.nvox > 0) {
+            MB_CUDA(cudaEventRecord(d.ev0, stream));
+            rc = enqueue_combine(job, device, stream);
+            if (rc != MPDAF_B200_OK) return rc;
+            MB_CUDA(cudaEventRecord(d.ev1, stream));
+        }
+    } else {
+        MB_CUDA(cudaStreamSynchronize(cstream));  // counters zeroed before the slab streams start
+        if (job.a.nvox > 0) {
+            rc = run_slabs(*slab_src, job, device, out, outvar, expmap);
+            if (rc != MPDAF_B200_OK) return rc;
+        }
+    }
+    unsigned long long host_counts[2 * kGenericMax];
+    MB_CUDA(cudaMemcpyAsync(host_counts, d.counters, sizeof host_counts, cudaMemcpyDeviceToHost, cstream));
+    MB_CUDA(cudaStreamSynchronize(cstream));
+    if (location == MPDAF_B200_DEVICE && job.a.nvox > 0) {
+        float ms = 0.f;
+        MB_CUDA(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        g_last_kernel_ms = ms;
+    }
+    for (int i = 0; i < nfiles; i++) {
+        const unsigned long long v = host_counts[i], s = host_counts[kGenericMax + i];
+        if (sink.valid32) sink.valid32[i] += (int)v;
+        if (sink.valid64) sink.valid64[i] += (long long)v;
+        if (!job.median) {
+            if (sink.select32) sink.select32[i] += (int)s;
+            if (sink.select64) sink.select64[i] += (long long)s;
+        }
+    }
+    return MPDAF_B200_OK;
+}
+
+// Splits the newline-joined file list (merging.c:39-55) WITHOUT touching the buffer.
+std::vector<std::string> split_list(const char* input)
+{
+    std::vector<std::string> names;
+    const char* p = input;
+    while (*p) {
+        const char* e = std::strchr(p, '\n');
+        const size_t len = e ? (size_t)(e - p) : std::strlen(p);
+        if (len > 0) names.emplace_back(p, len);
+        p += len + (e ? 1 : 0);
+    }
+    return names;
+}
+
+int open_all(const std::vector<std::string>& names, const char* ext, std::vector<mbfits::ImageHdu>& hdus,
+             const long long* shape)
+{
+    std::string err;
+    for (const std::string& n : names) {
+        mbfits::ImageHdu h;
+        const int rc = mbfits::open_image(n, ext, &h, &err);
+        if (rc != MPDAF_B200_OK) return fail(rc, err);
+        hdus.push_back(h);
+        const long long* ref = shape ? shape : hdus[0].naxes;
+        if (h.naxes[0] != ref[0] || h.naxes[1] != ref[1] || h.naxes[2] != ref[2])  // merging.c:195-199
+            return fail(MPDAF_B200_ERR_SHAPE, n + "[" + ext + "] does not have the same size");
+        if (h.bitpix != hdus[0].bitpix) return fail(MPDAF_B200_ERR_SHAPE, n + ": mixed BITPIX in one list");
+    }
+    return MPDAF_B200_OK;
+}
+
+int merge_files(char* input, bool median, double* data, double* var, int* expmap, double* scale, double* offset,
+                int* selected_pix, int* valid_pix, int nmax, double lo, double up, int nstop, int typ_var, int mad)
+{
+    if (!input || !data || !expmap || !valid_pix) return fail(MPDAF_B200_ERR_ARG, "null argument");
+    if (!median && (!var || !selected_pix)) return fail(MPDAF_B200_ERR_ARG, "null argument");
+    const std::vector<std::string> names = split_list(input);
+    if (names.empty()) return fail(MPDAF_B200_ERR_ARG, "empty file list");
+    if ((int)names.size() > MPDAF_B200_MAX_FILES) return fail(MPDAF_B200_ERR_ARG, "too many files, limit is 500");  // merging.c:46
+    std::vector<mbfits::ImageHdu> hd, hv;
+    struct Closer {
+        std::vector<mbfits::ImageHdu>&a, &b;
+        ~Closer() { for (auto& h : a) mbfits::close_image(&h); for (auto& h : b) mbfits::close_image(&h); }
+    } closer{hd, hv};
+    int rc = open_all(names, "DATA", hd, nullptr);
+    if (rc != MPDAF_B200_OK) return rc;
+    if (!median && typ_var == 0) {
+        rc = open_all(names, "STAT", hv, hd[0].naxes);
+        if (rc != MPDAF_B200_OK) return rc;
+        if (hv[0].bitpix != hd[0].bitpix) return fail(MPDAF_B200_ERR_SHAPE, "DATA and STAT differ in BITPIX");
+    }
+    Job job;
+    job.nfiles = (int)names.size();
+    job.elem = hd[0].bitpix == -32 ? MPDAF_B200_F32 : MPDAF_B200_F64;
+    job.median = median;
+    job.scale = scale;
+    job.offset = offset;
+    job.a.nfiles = job.nfiles;
+    job.a.nvox = hd[0].naxes[0] * hd[0].naxes[1] * hd[0].naxes[2];
+    job.a.nmax = nmax;
+    job.a.nclip_low = lo;
+    job.a.nclip_up = up;
+    job.a.nstop = nstop;
+    job.a.typ_var = median ? 1 : typ_var;
+    job.a.mad = mad;
+    SlabSource src;
+    src.fits_data = &hd;
+    src.fits_var = &hv;
+    CounterSink sink;
+    sink.valid32 = valid_pix;
+    sink.select32 = selected_pix;
+    const int device = (int)env_ll("MPDAF_B200_DEVICE", 0);
+    return run_job(job, &src, MPDAF_B200_HOST, device, data, var, expmap, sink, nullptr);
+}
+
+int merge_arrays(int nfiles, const void* const* data, const void* const* var, int elem_type, long long nvox,
+                 int location, int device, bool median, double* out, double* outvar, int* expmap,
+                 const double* scale, const double* offset, CounterSink sink, int nmax, double lo, double up,
+                 int nstop, int typ_var, int mad, void* stream)
+{
+    int rc = check_common(nfiles, data, elem_type, nvox, location);
+    if (rc != MPDAF_B200_OK) return rc;
+    if (nvox > 0 && (!out || !expmap || (!median && !outvar))) return fail(MPDAF_B200_ERR_ARG, "null output pointer");
+    if (!median && typ_var == 0) {
+        if (!var) return fail(MPDAF_B200_ERR_ARG, "var='propagate' needs the STAT arrays");
+        for (int i = 0; i < nfiles; i++)
+            if (!var[i] && nvox > 0) return fail(MPDAF_B200_ERR_ARG, "null STAT pointer");
+    }
+    Job job;
+    job.nfiles = nfiles;
+    job.elem = elem_type;
+    job.median = median;
+    job.data = data;
+    job.var = (!median && typ_var == 0) ? var : nullptr;
+    job.scale = scale;
+    job.offset = offset;
+    job.a.nfiles = nfiles;
+    job.a.nvox = nvox;
+    job.a.nmax = nmax;
+    job.a.nclip_low = lo;
+    job.a.nclip_up = up;
+    job.a.nstop = nstop;
+    job.a.typ_var = median ? 1 : typ_var;
+    job.a.mad = mad;
+    SlabSource src;
+    src.host_data = data;
+    src.host_var = var;
+    return run_job(job, &src, location, device, out, outvar, expmap, sink, (cudaStream_t)stream);
+}
+
+__global__ void synth_kernel(uint32_t* dst, int kind, unsigned long long seed, int exposure, long long v0,
+                             long long count, int nx, int ny)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+        dst[i] = kind == 0 ? mbsynth::data_bits(seed, exposure, v0 + i, nx, ny)
+                           : mbsynth::stat_bits(seed, exposure, v0 + i);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// exported symbols
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int mpdaf_merging_median(char* input, double* data, int* expmap, int* valid_pix)
+{
+    return merge_files(input, true, data, nullptr, expmap, nullptr, nullptr, nullptr, valid_pix, 0, 0, 0, 1, 1, 0);
+}
+
+int mpdaf_merging_sigma_clipping(char* input, double* data, double* var, int* expmap, double* scale,
+                                 double* offset, int* selected_pix, int* valid_pix, int nmax,
+                                 double nclip_low, double nclip_up, int nstop, int typ_var, int mad)
+{
+    return merge_files(input, false, data, var, expmap, scale, offset, selected_pix, valid_pix, nmax, nclip_low,
+                       nclip_up, nstop, typ_var, mad);
+}
+
+int mpdaf_b200_sigma_clipping_arrays(int nfiles, const void* const* data, const void* const* var, int elem_type,
+                                     long long nvox, int location, int device, double* out, double* outvar,
+                                     int* expmap, const double* scale, const double* offset, int* selected_pix,
+                                     int* valid_pix, int nmax, double nclip_low, double nclip_up, int nstop,
+                                     int typ_var, int mad, void* stream)
+{
+    if (!selected_pix || !valid_pix) return fail(MPDAF_B200_ERR_ARG, "null counter pointer");
+    CounterSink sink;
+    sink.valid32 = valid_pix;
+    sink.select32 = selected_pix;
+    return merge_arrays(nfiles, data, var, elem_type, nvox, location, device, false, out, outvar, expmap, scale,
+                        offset, sink, nmax, nclip_low, nclip_up, nstop, typ_var, mad, stream);
+}
+
+int mpdaf_b200_sigma_clipping_arrays64(int nfiles, const void* const* data, const void* const* var, int elem_type,
+                                       long long nvox, int location, int device, double* out, double* outvar,
+                                       int* expmap, const double* scale, const double* offset,
+                                       long long* selected_pix, long long* valid_pix, int nmax, double nclip_low,
+                                       double nclip_up, int nstop, int typ_var, int mad, void* stream)
+{
+    if (!selected_pix || !valid_pix) return fail(MPDAF_B200_ERR_ARG, "null counter pointer");
+    CounterSink sink;
+    sink.valid64 = valid_pix;
+    sink.select64 = selected_pix;
+    return merge_arrays(nfiles, data, var, elem_type, nvox, location, device, false, out, outvar, expmap, scale,
+                        offset, sink, nmax, nclip_low, nclip_up, nstop, typ_var, mad, stream);
+}
+
+int mpdaf_b200_median_arrays(int nfiles, const void* const* data, int elem_type, long long nvox, int location,
+                             int device, double* out, int* expmap, int* valid_pix, void* stream)
+{
+    if (!valid_pix) return fail(MPDAF_B200_ERR_ARG, "null counter pointer");
+    CounterSink sink;
+    sink.valid32 = valid_pix;
+    return merge_arrays(nfiles, data, nullptr, elem_type, nvox, location, device, true, out, nullptr, expmap,
+                        nullptr, nullptr, sink, 0, 0, 0, 1, 1, 0, stream);
+}
+
+double mpdaf_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+int mpdaf_b200_last_launch_count(void) { return g_last_launches; }
+const char* mpdaf_b200_last_kernel_name(void) { return g_last_kernel.c_str(); }
+const char* mpdaf_b200_last_error(void) { return g_error.c_str(); }
+
+int mpdaf_b200_device_count(void)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    int usable = 0;
+    for (int i = 0; i < count; i++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) usable++;
+    }
+    return usable;
+}
+
+int mpdaf_b200_fits_image_info(const char* path, const char* extname, long naxes[3], int* bitpix,
+                               long long* data_offset)
+{
+    if (!path || !extname || !naxes) return fail(MPDAF_B200_ERR_ARG, "null argument");
+    mbfits::ImageHdu h;
+    std::string err;
+    const int rc = mbfits::open_image(path, extname, &h, &err);
+    if (rc != MPDAF_B200_OK) return fail(rc, err);
+    for (int k = 0; k < 3; k++) naxes[k] = (long)h.naxes[k];
+    if (bitpix) *bitpix = h.bitpix;
+    if (data_offset) *data_offset = h.data_offset;
+    mbfits::close_image(&h);
+    return MPDAF_B200_OK;
+}
+
+int mpdaf_b200_synth_fill(void* dst, int location, int device, int kind, unsigned long long seed, int exposure,
+                          long long v0, long long count, int nx, int ny, void* stream)
+{
+    if (!dst || count < 0 || nx < 1 || ny < 1 || (kind != 0 && kind != 1)) return fail(MPDAF_B200_ERR_ARG, "bad synth argument");
+    if (location == MPDAF_B200_HOST) {
+        uint32_t* p = static_cast<uint32_t*>(dst);
+        const int nthreads = (int)std::max(1LL, std::min<long long>(std::thread::hardware_concurrency(), count / 65536 + 1));
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; t++)
+            pool.emplace_back([=]() {
+                const long long lo = count * t / nthreads, hi = count * (t + 1) / nthreads;
+                for (long long i = lo; i < hi; i++)
+                    p[i] = kind == 0 ? mbsynth::data_bits(seed, exposure, v0 + i, nx, ny)
+                                     : mbsynth::stat_bits(seed, exposure, v0 + i);
+            });
+        for (auto& th : pool) th.join();
+        return MPDAF_B200_OK;
+    }
+    const int rc = device_ready(device);
+    if (rc != MPDAF_B200_OK) return rc;
+    if (count == 0) return MPDAF_B200_OK;
+    const int grid = (int)std::min<long long>((count + 255) / 256, (long long)g_dev[device].sm_count * 16);
+    synth_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<uint32_t*>(dst), kind, seed, exposure, v0,
+                                                         count, nx, ny);
+    MB_CUDA(cudaGetLastError());
+    return MPDAF_B200_OK;
+}
+
+}  // extern "C"

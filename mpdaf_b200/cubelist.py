@@ -1,0 +1,449 @@
+"""Host side of the combine path: a `CubeList` with the reference's interface.
+
+Mirrors lib/mpdaf/obj/cubelist.py of the reference for the two methods on the
+hot path, `CubeList.median` (:432-468) and `CubeList.combine` (:470-536): same
+arguments, same defaults (nmax=2, nclip=5.0, nstop=2, var='propagate',
+mad=False), same output allocation and marshalling, the same
+`(cube, expmap, statpix)` return, the same `statpix` arithmetic (:459-461,
+:518-524), `_compute_expnb` (:69-74) and `save_combined_cube` header logic
+(:392-430).  The work itself is done by the CUDA `_ctools` library through the
+ctypes loader `mpdaf_b200.ctools` (the reference's `mpdaf.tools.ctools`).
+
+astropy is not available in this image, so `Cube` here is a light container
+(data / var ndarray, primary and data header dicts, `write`) rather than
+`mpdaf.obj.Cube`, and `statpix` is a small column table; with astropy installed
+`StatTable.to_astropy()` gives the reference's `astropy.table.Table`.
+
+Besides FITS file names, a list can be built from in-memory exposure stacks
+(`CubeList.from_arrays`), host NumPy arrays or device pointers, which is how the
+FITS decoding stays outside the timed region in bench.py.
+"""
+import ctypes
+import logging
+import os
+from ctypes import c_char_p
+
+import numpy as np
+
+from . import fits as _fits
+
+__all__ = ('CubeList', 'Cube', 'StatTable', 'DeviceStack')
+
+__version__ = '0.1'
+
+# List of keywords copied to the combined cube (reference cubelist.py:52-66)
+KEYWORDS_TO_COPY = (
+    'ORIGIN', 'TELESCOP', 'INSTRUME', 'RA', 'DEC', 'EQUINOX', 'RADECSYS',
+    'EXPTIME', 'MJD-OBS', 'DATE-OBS', 'PI-COI', 'OBSERVER', 'OBJECT',
+    'HIERARCH ESO INS DROT POSANG',
+    'HIERARCH ESO INS MODE',
+    'HIERARCH ESO DET READ CURID',
+    'HIERARCH ESO INS TEMP11 VAL',
+    'HIERARCH ESO OBS ID',
+    'HIERARCH ESO OBS NAME',
+    'HIERARCH ESO OBS START',
+    'HIERARCH ESO TEL AIRM END',
+    'HIERARCH ESO TEL AIRM START',
+    'HIERARCH ESO TEL AMBI FWHM END',
+    'HIERARCH ESO TEL AMBI FWHM START'
+)
+
+
+def _compute_expnb(expmap):
+    """Most frequent non-zero exposure count (reference cubelist.py:69-74).
+
+    scipy.stats.mode returns the smallest of tied modes; the first maximum of a
+    histogram does the same in one pass over the int32 map."""
+    counts = np.bincount(np.asarray(expmap).ravel())
+    if counts.size <= 1 or counts[1:].max() == 0:
+        return 0
+    return int(np.argmax(counts[1:])) + 1
+
+
+def _add_method_keywords(header, method, params, values, comments):
+    """HIERARCH MPDAF METHn provenance block (reference tools/fits.py:54-89)."""
+    i = 1
+    while 'HIERARCH MPDAF METH%d ID' % i in header:
+        i += 1
+    header['HIERARCH MPDAF METH%d VERSION' % i] = (__version__, 'MPDAF version')
+    header['HIERARCH MPDAF METH%d ID' % i] = (method, 'MPDAF method identifier')
+    for p, (name, value, comment) in enumerate(zip(params, values, comments)):
+        header['HIERARCH MPDAF METH%d PARAM%d NAME' % (i, p + 1)] = (name, comment)
+        keyword = 'HIERARCH MPDAF METH%d PARAM%d VALUE' % (i, p + 1)
+        if isinstance(value, str):
+            value = value[0:80 - len(keyword) - 14]
+        elif isinstance(value, (bool, np.bool_)):
+            value = bool(value)
+        header[keyword] = value
+
+
+class Cube:
+    """Combined cube: `data` (nz, ny, nx), optional `var`, two header dicts."""
+
+    def __init__(self, data, var=None, primary_header=None, data_header=None, unit=None,
+                 filename=None, comments=()):
+        self.data = data
+        self.var = var
+        self.primary_header = dict(primary_header or {})
+        self.data_header = dict(data_header or {})
+        self.unit = unit
+        self.filename = filename
+        self.comments = list(comments)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def mask(self):
+        """True where the voxel holds no finite value (reference Cube masks ~isfinite)."""
+        return ~np.isfinite(self.data)
+
+    def write(self, filename, dtype=np.float32):
+        """PRIMARY + DATA [+ STAT] float32 images, NaN for empty voxels (savemask='nan')."""
+        _fits.write_cube(filename, self.data, self.var, self.primary_header, self.data_header,
+                         dtype=dtype, comments=self.comments)
+        self.filename = filename
+
+
+class StatTable:
+    """Column table standing in for astropy.table.Table (FILENAME, NPIX_NAN, ...)."""
+
+    def __init__(self, columns, names):
+        self.colnames = list(names)
+        self._cols = {n: np.asarray(c) for n, c in zip(names, columns)}
+
+    def __getitem__(self, name):
+        return self._cols[name]
+
+    def __len__(self):
+        return len(next(iter(self._cols.values())))
+
+    def to_astropy(self):
+        from astropy.table import Table
+        return Table([self._cols[n] for n in self.colnames], names=self.colnames)
+
+    def __repr__(self):
+        rows = ["  ".join(self.colnames)]
+        for r in range(len(self)):
+            rows.append("  ".join(str(self._cols[n][r]) for n in self.colnames))
+        return "\n".join(rows)
+
+
+class DeviceStack:
+    """Exposure stack resident in device memory: raw pointers + geometry.
+
+    data_ptrs / var_ptrs: one device address per exposure (nvox float32 or float64
+    samples each, x fastest).  `keepalive` holds whatever owns the memory."""
+
+    def __init__(self, data_ptrs, var_ptrs, shape, elem_type=4, device=0, keepalive=None):
+        self.data_ptrs = [int(p) for p in data_ptrs]
+        self.var_ptrs = None if var_ptrs is None else [int(p) for p in var_ptrs]
+        self.shape = tuple(int(s) for s in shape)
+        self.elem_type = int(elem_type)
+        self.device = int(device)
+        self.keepalive = keepalive
+
+
+def _ptr_table(addresses):
+    arr = (ctypes.c_void_p * len(addresses))(*addresses)
+    return arr, ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+
+
+class CubeList:
+
+    """Manages a list of cubes and handles the combination.
+
+    To run the combination, all the cubes must have the same dimensions and be
+    on the same WCS grid. A global flux offset and scale can be given for each
+    cube: ``(data + offset) * scale``.
+
+    Parameters
+    ----------
+    files : list of str
+        List of cubes FITS filenames.
+    scalelist: list of float, optional
+        List of scales to be applied to each cube.
+    offsetlist: list of float, optional
+        List of offsets to be applied to each cube.
+
+    Attributes
+    ----------
+    files, nfiles, flux_scales, flux_offsets, shape : as in the reference
+    (lib/mpdaf/obj/cubelist.py:268-303); wcs / wave objects are out of scope, the
+    WCS keywords of cube 0's DATA header are carried over verbatim instead.
+    """
+
+    checkers = ('check_dim',)
+
+    def __init__(self, files, scalelist=None, offsetlist=None):
+        self._logger = logging.getLogger(__name__)
+        self.files = list(files)
+        self.nfiles = len(self.files)
+        self._stack = None
+        self._host_arrays = None
+
+        # headers only, like DataArray's lazy loading (data.py:57-104)
+        self._headers = []
+        for f in self.files:
+            hdus = _fits.read_hdus(f)
+            data_hdr = next((h for h, _, _ in hdus if str(h.get('EXTNAME', '')).upper() == 'DATA'), None)
+            if data_hdr is None:
+                raise OSError(f'{f}: no DATA extension')
+            self._headers.append((hdus[0][0], data_hdr))
+        self._set_defaults()
+        self.check_compatibility()
+
+        self.flux_scales = scalelist
+        self.flux_offsets = offsetlist
+
+    @classmethod
+    def from_arrays(cls, data, var=None, scalelist=None, offsetlist=None, names=None,
+                    primary_header=None, data_header=None):
+        """Build a list from in-memory exposures instead of FITS files.
+
+        data / var: sequences of equally shaped (nz, ny, nx) float32 or float64
+        C-contiguous NumPy arrays, or a `DeviceStack`."""
+        self = cls.__new__(cls)
+        self._logger = logging.getLogger(__name__)
+        if isinstance(data, DeviceStack):
+            self._stack = data
+            self._host_arrays = None
+            self.nfiles = len(data.data_ptrs)
+            self.shape = tuple(data.shape)
+        else:
+            arrays = [np.ascontiguousarray(a) for a in data]
+            dt = arrays[0].dtype
+            if dt not in (np.float32, np.float64) or any(a.dtype != dt or a.shape != arrays[0].shape for a in arrays):
+                raise ValueError('exposures must share one shape and be float32 or float64')
+            vars_ = None
+            if var is not None:
+                vars_ = [np.ascontiguousarray(a, dtype=dt) for a in var]
+                if len(vars_) != len(arrays) or any(a.shape != arrays[0].shape for a in vars_):
+                    raise ValueError('var must match data')
+            self._stack = None
+            self._host_arrays = (arrays, vars_)
+            self.nfiles = len(arrays)
+            self.shape = tuple(arrays[0].shape)
+        self.files = list(names) if names is not None else ['exposure-%03d' % i for i in range(self.nfiles)]
+        self._headers = [(dict(primary_header or {}), dict(data_header or {}))] * self.nfiles
+        self.unit = None
+        self.flux_scales = scalelist
+        self.flux_offsets = offsetlist
+        return self
+
+    def _set_defaults(self):
+        h = self._headers[0][1]
+        self.shape = (int(h['NAXIS3']), int(h['NAXIS2']), int(h['NAXIS1']))
+        self.unit = h.get('BUNIT')
+
+    def check_dim(self):
+        """Checks if all cubes have same dimensions."""
+        shapes = np.array([(int(h['NAXIS3']), int(h['NAXIS2']), int(h['NAXIS1'])) for _, h in self._headers])
+        if not np.all(shapes == self.shape):
+            self._logger.warning('all cubes have not same dimensions')
+            for i in range(self.nfiles):
+                self._logger.warning('%i X %i X %i cube (%s)', shapes[i, 0], shapes[i, 1], shapes[i, 2],
+                                     self.files[i])
+            return False
+        return True
+
+    def check_compatibility(self):
+        """Checks if all cubes are compatible."""
+        for checker in self.checkers:
+            getattr(self, checker)()
+
+    # ------------------------------------------------------------------
+    def save_combined_cube(self, data, var=None, method='', keywords=None, expnb=None, unit=None,
+                           header=None):
+        if data.ndim != 3:
+            data = data.reshape(self.shape)
+        if var is not None and var.ndim != 3:
+            var = var.reshape(self.shape)
+
+        src_primary, src_data = self._headers[0]
+        hdr = {}
+        for key in KEYWORDS_TO_COPY:
+            if key in src_primary:
+                hdr[key] = src_primary[key]
+        if expnb is not None and 'EXPTIME' in hdr:
+            hdr['EXPTIME'] = hdr['EXPTIME'] * expnb
+        if header is not None:
+            hdr.update(header)
+
+        data_header = {k: v for k, v in src_data.items()
+                       if k.startswith(('CRPIX', 'CRVAL', 'CDELT', 'CD1_', 'CD2_', 'CD3_', 'CTYPE', 'CUNIT'))}
+        if unit is None and self.unit is not None:
+            data_header['BUNIT'] = self.unit
+        if 'OBJECT' in hdr:
+            data_header['OBJECT'] = hdr['OBJECT']
+        elif 'OBJECT' in src_data:
+            data_header['OBJECT'] = src_data['OBJECT']
+
+        if keywords is not None:
+            params, values, comments = list(zip(*keywords))
+        else:
+            params, values, comments = [], [], []
+        _add_method_keywords(hdr, method, params, values, comments)
+        hdr['NFILES'] = (len(self.files), 'number of files merged in the cube')
+
+        comments_out = ['List of cubes merged in this cube:']
+        comments_out += ['- ' + os.path.basename(f) for f in self.files]
+        return Cube(data, var=var, primary_header=hdr, data_header=data_header, unit=unit or self.unit,
+                    comments=comments_out)
+
+    # ------------------------------------------------------------------
+    def _scales_offsets(self):
+        if self.flux_scales is None:
+            scale = np.ones(self.nfiles, dtype=float)
+        else:
+            scale = np.asarray(self.flux_scales, dtype=float)
+            self._logger.info('Using scales')
+        if self.flux_offsets is None:
+            offset = np.zeros(self.nfiles, dtype=float)
+        else:
+            offset = np.asarray(self.flux_offsets, dtype=float)
+            self._logger.info('Using offsets')
+        return scale, offset
+
+    def median(self, header=None):
+        """Combines cubes in a single data cube using median.
+
+        Returns
+        -------
+        out : Cube, Cube, StatTable
+            cube, expmap, statpix (columns FILENAME and NPIX_NAN)
+        """
+        from .ctools import ctools, check, HOST
+
+        npixels = int(np.prod(self.shape))
+        data = np.empty(npixels, dtype=np.float64, order='C')
+        expmap = np.empty(npixels, dtype=np.intc, order='C')
+        valid_pix = np.zeros(self.nfiles, dtype=np.intc, order='C')
+
+        if self._host_arrays is None and self._stack is None:
+            files = '\n'.join(self.files).encode('utf8')
+            rc = ctools.mpdaf_merging_median(c_char_p(files), data, expmap, valid_pix)
+            check(rc, 'mpdaf_merging_median')
+        elif self._host_arrays is not None:
+            arrays, _ = self._host_arrays
+            keep, dptr = _ptr_table([a.ctypes.data for a in arrays])
+            rc = ctools.mpdaf_b200_median_arrays(
+                self.nfiles, dptr, arrays[0].dtype.itemsize, npixels, HOST, 0,
+                data.ctypes.data, expmap.ctypes.data, valid_pix, None)
+            check(rc, 'mpdaf_b200_median_arrays')
+        else:
+            data, _, expmap = self._run_device_stack(True, valid_pix, None)
+
+        no_valid_pix = npixels - valid_pix
+        stat_pix = StatTable([self.files, no_valid_pix], names=['FILENAME', 'NPIX_NAN'])
+
+        kwargs = dict(expnb=_compute_expnb(expmap), method='obj.cubelist.median', header=header)
+        expmap = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
+        cube = self.save_combined_cube(data, **kwargs)
+        return cube, expmap, stat_pix
+
+    def combine(self, nmax=2, nclip=5.0, nstop=2, var='propagate', mad=False, header=None):
+        """Combines cubes in a single data cube using sigma clipped mean.
+
+        Same parameters and return as the reference (cubelist.py:219-254, :470-536):
+        nmax, nclip (scalar or (low, up)), nstop, var in {'propagate', 'stat_mean',
+        'stat_one'}, mad.  Returns cube, expmap, statpix (FILENAME, NPIX_NAN,
+        NPIX_REJECTED).
+        """
+        from .ctools import ctools, check, HOST
+
+        if np.isscalar(nclip):
+            nclip_low = nclip
+            nclip_up = nclip
+        else:
+            nclip_low = nclip[0]
+            nclip_up = nclip[1]
+
+        npixels = self.shape[0] * self.shape[1] * self.shape[2]
+        data = np.empty(npixels, dtype=np.float64, order='C')
+        vardata = np.empty(npixels, dtype=np.float64, order='C')
+        expmap = np.empty(npixels, dtype=np.intc, order='C')
+        valid_pix = np.zeros(self.nfiles, dtype=np.intc, order='C')
+        select_pix = np.zeros(self.nfiles, dtype=np.intc, order='C')
+
+        if var == 'propagate':
+            var_mean = 0
+        elif var == 'stat_mean':
+            var_mean = 1
+        else:
+            var_mean = 2
+
+        scale, offset = self._scales_offsets()
+        params = (nmax, np.float64(nclip_low), np.float64(nclip_up), nstop, np.int32(var_mean), np.int32(mad))
+
+        if self._host_arrays is None and self._stack is None:
+            files = '\n'.join(self.files).encode('utf8')
+            rc = ctools.mpdaf_merging_sigma_clipping(
+                c_char_p(files), data, vardata, expmap, scale, offset, select_pix, valid_pix, *params)
+            check(rc, 'mpdaf_merging_sigma_clipping')
+        elif self._host_arrays is not None:
+            arrays, vars_ = self._host_arrays
+            if var_mean == 0 and vars_ is None:
+                raise ValueError("var='propagate' needs the exposure variances")
+            keep_d, dptr = _ptr_table([a.ctypes.data for a in arrays])
+            keep_v, vptr = (None, None) if vars_ is None else _ptr_table([a.ctypes.data for a in vars_])
+            rc = ctools.mpdaf_b200_sigma_clipping_arrays(
+                self.nfiles, dptr, vptr, arrays[0].dtype.itemsize, npixels, HOST, 0,
+                data.ctypes.data, vardata.ctypes.data, expmap.ctypes.data,
+                scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix,
+                int(nmax), float(nclip_low), float(nclip_up), int(nstop), int(var_mean), int(mad), None)
+            check(rc, 'mpdaf_b200_sigma_clipping_arrays')
+        else:
+            data, vardata, expmap = self._run_device_stack(
+                False, valid_pix, select_pix, scale, offset,
+                (int(nmax), float(nclip_low), float(nclip_up), int(nstop), int(var_mean), int(mad)))
+
+        # no valid pixels
+        with np.errstate(divide='ignore', invalid='ignore'):
+            rej = (valid_pix - select_pix) / valid_pix.astype(float) * 100.0
+        rej = " ".join(f"{p:.2f}%" for p in rej)
+        self._logger.info("%% of rejected pixels per files: %s", rej)
+        no_valid_pix = npixels - valid_pix
+        rejected_pix = valid_pix - select_pix
+        statpix = StatTable([self.files, no_valid_pix, rejected_pix],
+                            names=['FILENAME', 'NPIX_NAN', 'NPIX_REJECTED'])
+
+        keywords = [('nmax', nmax, 'max number of clipping iterations'),
+                    ('nclip_low', nclip_low, 'lower clipping parameter'),
+                    ('nclip_up', nclip_up, 'upper clipping parameter'),
+                    ('nstop', nstop, 'clipping minimum number'),
+                    ('var', var, 'type of variance')]
+        kwargs = dict(expnb=_compute_expnb(expmap), keywords=keywords, header=header,
+                      method='obj.cubelist.merging')
+        expmap = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
+        cube = self.save_combined_cube(data, var=vardata, **kwargs)
+        return cube, expmap, statpix
+
+    # ------------------------------------------------------------------
+    def _run_device_stack(self, median, valid_pix, select_pix, scale=None, offset=None, params=None):
+        """Device-resident stack: outputs are produced on the device and read back."""
+        import torch
+        from .ctools import ctools, check, DEVICE
+
+        st = self._stack
+        npixels = int(np.prod(st.shape))
+        dev = torch.device('cuda', st.device)
+        out = torch.empty(npixels, dtype=torch.float64, device=dev)
+        expmap = torch.empty(npixels, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        keep_d, dptr = _ptr_table(st.data_ptrs)
+        if median:
+            rc = ctools.mpdaf_b200_median_arrays(
+                self.nfiles, dptr, st.elem_type, npixels, DEVICE, st.device,
+                out.data_ptr(), expmap.data_ptr(), valid_pix, stream)
+            check(rc, 'mpdaf_b200_median_arrays')
+            return out.cpu().numpy(), None, expmap.cpu().numpy()
+        outvar = torch.empty(npixels, dtype=torch.float64, device=dev)
+        keep_v, vptr = (None, None) if st.var_ptrs is None else _ptr_table(st.var_ptrs)
+        rc = ctools.mpdaf_b200_sigma_clipping_arrays(
+            self.nfiles, dptr, vptr, st.elem_type, npixels, DEVICE, st.device,
+            out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(),
+            scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix, *params, stream)
+        check(rc, 'mpdaf_b200_sigma_clipping_arrays')
+        return out.cpu().numpy(), outvar.cpu().numpy(), expmap.cpu().numpy()
