@@ -1,0 +1,177 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+
+Sizes are chosen so the oracle finishes in seconds.  Bit-exact: expmap, per-exposure
+counters, medians, NaN positions.  <= 1e-6 relative: sigma-clipped means and variances.
+"""
+import ctypes
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import assert_same_result, random_stack, write_exposures
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda():
+    import cuda_runner
+    return cuda_runner
+
+
+@pytest.mark.parametrize("location", ["device", "host"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 12, 13, 16, 24, 25, 32, 33, 48, 49, 64])
+def test_register_kernels_every_bucket(n, location):
+    rng = np.random.default_rng(100 + n)
+    shape = (6, 11, 13)          # 858 voxels: not a multiple of the block size
+    data, var = random_stack(rng, n, shape, nan_frac=0.12, outlier_frac=0.04)
+    scales = np.linspace(0.9, 1.1, n)
+    offsets = np.linspace(-0.1, 0.1, n)
+    for kw in (dict(), dict(scales=scales, offsets=offsets)):
+        for vartype, nclip in (("propagate", 3.0), ("stat_mean", (2.0, 3.0)), ("stat_one", 5.0)):
+            want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, **kw)
+            got = cuda().combine_cuda(data, var, vartype=vartype, nclip=nclip, location=location, **kw)
+            assert_same_result(got, want)
+            assert "reg" in cuda().kernel_name()
+    want = oracle.median_port(data)
+    got = cuda().median_cuda(data, location=location)
+    assert_same_result(got, want, median=True)
+
+
+def test_unit_scale_path_is_bit_exact():
+    """Without scales/offsets the sums run in the reference's order: data identical to the bit."""
+    rng = np.random.default_rng(5)
+    data, var = random_stack(rng, 48, (5, 9, 10), nan_frac=0.05, outlier_frac=0.03)
+    for nclip in (5.0, 3.0, 2.0):
+        want = oracle.combine_port(data, var, nclip=nclip, vartype="stat_one")
+        got = cuda().combine_cuda(data, var, nclip=nclip, vartype="stat_one")
+        assert "unit" in cuda().kernel_name()
+        assert_same_result(got, want, exact_data=True)
+        np.testing.assert_array_equal(got["var"], want["var"])
+        assert (want["select_pix"] < want["valid_pix"]).any()
+
+
+def test_scaled_path_is_bit_exact_too():
+    rng = np.random.default_rng(6)
+    n = 24
+    data, var = random_stack(rng, n, (5, 9, 10), nan_frac=0.05, outlier_frac=0.05)
+    want = oracle.combine_port(data, var, scales=np.linspace(0.5, 2, n), offsets=np.linspace(-3, 3, n),
+                               nclip=2.5, vartype="stat_mean")
+    got = cuda().combine_cuda(data, var, scales=np.linspace(0.5, 2, n), offsets=np.linspace(-3, 3, n),
+                              nclip=2.5, vartype="stat_mean")
+    assert "scaled" in cuda().kernel_name()
+    assert_same_result(got, want, exact_data=True)
+
+
+@pytest.mark.parametrize("nmax,lo,up,nstop", [(0, 2.0, 2.0, 2), (1, 1.5, 3.0, 1), (3, 1.0, 1.0, 3),
+                                              (2, 3.0, 1.5, 5), (5, 1.2, 1.2, 2), (2, 0.5, 0.5, 1),
+                                              (2, 5.0, 5.0, 0), (10, 1.0, 2.0, 2)])
+@pytest.mark.parametrize("ties", [False, True])
+def test_clip_parameters(nmax, lo, up, nstop, ties):
+    rng = np.random.default_rng(nmax * 31 + nstop)
+    data, var = random_stack(rng, 16, (4, 8, 9), nan_frac=0.2, outlier_frac=0.1, ties=ties)
+    if nstop < 1:
+        # nstop >= 1 is a precondition of the reference (ni == 0 would recurse on an empty
+        # set); the replacement treats nstop < 1 as 1.
+        want = oracle.combine_port(data, var, nmax=nmax, nclip=(lo, up), nstop=1, vartype="stat_one")
+    else:
+        want = oracle.combine_port(data, var, nmax=nmax, nclip=(lo, up), nstop=nstop, vartype="stat_one")
+    got = cuda().combine_cuda(data, var, nmax=nmax, nclip=(lo, up), nstop=nstop, vartype="stat_one")
+    assert_same_result(got, want)
+
+
+@pytest.mark.parametrize("n", [5, 48, 70, 130])
+@pytest.mark.parametrize("vartype", ["propagate", "stat_mean"])
+def test_mad_and_deep_stacks_use_the_generic_kernels(n, vartype):
+    rng = np.random.default_rng(n)
+    data, var = random_stack(rng, n, (3, 5, 7), nan_frac=0.1, outlier_frac=0.05)
+    kw = dict(scales=np.linspace(0.9, 1.1, n), offsets=np.linspace(-0.1, 0.1, n), nclip=3.0, vartype=vartype)
+    for mad in (True, False):
+        want = oracle.combine_port(data, var, mad=mad, **kw)
+        got = cuda().combine_cuda(data, var, mad=mad, **kw)
+        assert_same_result(got, want)
+        if mad or n > 64:
+            assert "generic" in cuda().kernel_name()
+    if n > 64:
+        assert_same_result(cuda().median_cuda(data), oracle.median_port(data), median=True)
+
+
+@pytest.mark.parametrize("location", ["device", "host"])
+def test_float64_exposures(location):
+    rng = np.random.default_rng(8)
+    data, var = random_stack(rng, 7, (4, 5, 6), dtype=np.float64)
+    want = oracle.combine_port(data, var, nclip=2.0)
+    got = cuda().combine_cuda(data, var, nclip=2.0, location=location)
+    assert_same_result(got, want)
+    assert_same_result(cuda().median_cuda(data, location=location), oracle.median_port(data), median=True)
+
+
+def test_edge_cases():
+    c = cuda()
+    # empty stack
+    empty = [np.zeros((0, 3, 3), dtype=np.float32)] * 3
+    got = c.combine_cuda(empty, empty)
+    assert got["data"].size == 0 and (got["valid_pix"] == 0).all()
+    # every sample NaN / exactly one valid exposure / constant data (sigma == 0)
+    shape = (2, 3, 4)
+    nan = np.full(shape, np.nan, dtype=np.float32)
+    one = np.full(shape, 7.5, dtype=np.float32)
+    for stack in ([nan, nan, nan], [nan, one, nan], [one, one, one, one], [one]):
+        var = [np.full(shape, 2.0, dtype=np.float32) for _ in stack]
+        for vartype in ("propagate", "stat_mean", "stat_one"):
+            want = oracle.combine_port(stack, var, vartype=vartype, scales=[2.0] * len(stack))
+            got = c.combine_cuda(stack, var, vartype=vartype, scales=[2.0] * len(stack))
+            assert_same_result(got, want, exact_data=True)
+        assert_same_result(c.median_cuda(stack), oracle.median_port(stack), median=True)
+    # ragged NaN pattern: exposure i misses the first i planes entirely
+    rng = np.random.default_rng(1)
+    data, var = random_stack(rng, 6, (8, 4, 4), nan_frac=0.0)
+    for i, d in enumerate(data):
+        d[:i] = np.nan
+    assert_same_result(c.combine_cuda(data, var, nclip=2.0), oracle.combine_port(data, var, nclip=2.0))
+    # counters are ADDED to caller values (merging.c:486-491): run twice through one buffer
+    r1 = c.combine_cuda(data, var, nclip=2.0)
+    assert (r1["valid_pix"] == oracle.combine_port(data, var, nclip=2.0)["valid_pix"]).all()
+
+
+def test_large_slab_multiple_chunks(monkeypatch):
+    """Host-location call with a tiny staging budget: many pipelined chunks, same result."""
+    monkeypatch.setenv("MPDAF_B200_SLAB_BYTES", str(1 << 20))
+    rng = np.random.default_rng(77)
+    data, var = random_stack(rng, 12, (40, 30, 31))
+    want = oracle.combine_port(data, var, nclip=3.0)
+    got = cuda().combine_cuda(data, var, nclip=3.0, location="host")
+    assert_same_result(got, want)
+    assert_same_result(cuda().median_cuda(data, location="host"), oracle.median_port(data), median=True)
+
+
+@pytest.mark.parametrize("vartype,mad", list(itertools.product(["propagate", "stat_mean", "stat_one"], [0, 1])))
+def test_dropin_file_symbols_against_reference(tmp_path, vartype, mad):
+    """The two symbols ctools.py binds, on FITS files, against the reference's own build."""
+    if not oracle.have_ref():
+        pytest.skip("reference build (oracle/_ref) not shipped")
+    from mpdaf_b200.ctools import ctools
+    rng = np.random.default_rng(21)
+    shape, n = (12, 9, 10), 6
+    data, var = random_stack(rng, n, shape, nan_frac=0.1, outlier_frac=0.06)
+    files = write_exposures(tmp_path, data, var)
+    scales, offsets = np.linspace(0.7, 1.2, n), np.linspace(-1, 1, n)
+    want = oracle.combine_ref(files, shape, scales=scales, offsets=offsets, nclip=(2.0, 2.5), vartype=vartype,
+                              mad=bool(mad))
+    nvox = int(np.prod(shape))
+    out, outvar = np.empty(nvox), np.empty(nvox)
+    expmap = np.empty(nvox, dtype=np.intc)
+    sel, val = np.zeros(n, dtype=np.intc), np.zeros(n, dtype=np.intc)
+    names = "\n".join(files).encode()
+    typ = {"propagate": 0, "stat_mean": 1, "stat_one": 2}[vartype]
+    rc = ctools.mpdaf_merging_sigma_clipping(ctypes.c_char_p(names), out, outvar, expmap, scales, offsets, sel, val,
+                                             2, 2.0, 2.5, 2, typ, mad)
+    assert rc == 0
+    assert names == "\n".join(files).encode()
+    assert_same_result(dict(data=out, var=outvar, expmap=expmap, select_pix=sel, valid_pix=val), want)
+    wantm = oracle.median_ref(files, shape)
+    val = np.zeros(n, dtype=np.intc)
+    rc = ctools.mpdaf_merging_median(ctypes.c_char_p(names), out, expmap, val)
+    assert rc == 0
+    assert_same_result(dict(data=out, expmap=expmap, valid_pix=val), wantm, median=True)
