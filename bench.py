@@ -295,7 +295,8 @@ def run_b200_arm(args):
     # size-independent sanity of the full-size result (cheap, outside the timed region)
     n_sel = int(select.astype(np.int64).sum())
     assert n_sel == int(expmap.sum(dtype=torch.int64).item()), "sum(expmap) != sum(selected_pix)"
-    assert int(valid.astype(np.int64).sum()) == int((~torch.isnan(tdata)).sum().item()), "valid_pix != #non-NaN samples"
+    for i in (0, NFILES // 2, NFILES - 1):
+        assert int(valid[i]) == nvox - int(torch.isnan(tdata[i]).sum().item()), "valid_pix != #non-NaN samples"
 
     # ---- e2e: same C-ABI call with HOST (pinned) buffers, copies inside the timed region
     nz_e = min(nz, args.e2e_nz)

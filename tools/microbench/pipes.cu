@@ -6,12 +6,14 @@
 #include <vector>
 
 constexpr int CH = 8;      // independent chains per thread
-constexpr int IT = 512;    // loop iterations
+constexpr int IT = 2048;    // loop iterations
 constexpr int TPB = 256;
 
 #define KERNEL(name, DECL, INIT, BODY, SINK)                                              \
     __global__ void name(unsigned long long* cyc, float* out, float seedf, double seedd, int seedi) \
     {                                                                                     \
+        unsigned smid;                                                                    \
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));                                 \
         DECL;                                                                             \
         _Pragma("unroll") for (int c = 0; c < CH; c++) { INIT; }                        \
         __syncthreads();                                                                  \
@@ -23,7 +25,11 @@ constexpr int TPB = 256;
         float acc = 0;                                                                    \
         _Pragma("unroll") for (int c = 0; c < CH; c++) { SINK; }                        \
         if (acc == 123.456f) out[0] = acc;                                                \
-        if (threadIdx.x == 0) cyc[blockIdx.x] = (unsigned long long)(t1 - t0);           \
+        if ((threadIdx.x & 31) == 0) {                                                    \
+            atomicMin(&cyc[smid], (unsigned long long)t0);                                \
+            atomicMax(&cyc[256 + smid], (unsigned long long)t1);                          \
+            atomicAdd(&cyc[512 + smid], 1ull);                                            \
+        }                                                                                 \
     }
 
 // ops per BODY instance noted beside each kernel
@@ -77,9 +83,12 @@ void run(const char* name, K kernel, double ops_per_body)
     const int grid = sms * bps;
     unsigned long long* cyc;
     float* out;
-    cudaMalloc(&cyc, grid * sizeof(unsigned long long));
+    cudaMalloc(&cyc, 768 * sizeof(unsigned long long));
     cudaMalloc(&out, 4);
+    std::vector<unsigned long long> init(768, 0ull);
+    for (int i = 0; i < 256; i++) init[i] = ~0ull;
     for (int rep = 0; rep < 2; rep++) kernel<<<grid, TPB>>>(cyc, out, 1.5f, 1.25, 3);
+    cudaMemcpy(cyc, init.data(), 768 * sizeof(unsigned long long), cudaMemcpyHostToDevice);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -89,14 +98,22 @@ void run(const char* name, K kernel, double ops_per_body)
     cudaDeviceSynchronize();
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    std::vector<unsigned long long> h(grid);
-    cudaMemcpy(h.data(), cyc, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    double mean = 0;
-    for (auto v : h) mean += (double)v;
-    mean /= grid;
-    const double bodies_per_sm = (double)bps * TPB * CH * IT;
-    printf("%-18s %8.1f lane-bodies/clk/SM  (%5.2f ops/body -> %7.1f lane-ops/clk/SM)  cycles=%.0f  %.3f ms  err=%s\n", name,
-           bodies_per_sm / mean, ops_per_body, bodies_per_sm * ops_per_body / mean, mean, ms,
+    std::vector<unsigned long long> h(768);
+    cudaMemcpy(h.data(), cyc, 768 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    // per SM: lane-bodies executed / (last warp end - first warp start)
+    double rate = 0, cycles = 0;
+    int used = 0;
+    for (int s = 0; s < 256; s++) {
+        if (h[512 + s] == 0) continue;
+        const double c = (double)(h[256 + s] - h[s]);
+        rate += (double)h[512 + s] * 32 * CH * IT / c;
+        cycles += c;
+        used++;
+    }
+    rate /= used;
+    cycles /= used;
+    printf("%-22s %7.1f lane-bodies/clk/SM (%4.1f ops/body -> %6.1f lane-ops/clk/SM)  SMs=%d cycles=%.0f  %.3f ms -> %.2f GHz  %s\n",
+           name, rate, ops_per_body, rate * ops_per_body, used, cycles, ms, cycles / (ms * 1e6),
            cudaGetErrorString(cudaGetLastError()));
     cudaFree(cyc);
     cudaFree(out);
