@@ -130,6 +130,10 @@ int mpdaf_b200_last_launch_count(void);
 /* Name of the kernel family the last call dispatched to ("sigclip_reg<48,unit>" ...). */
 const char *mpdaf_b200_last_kernel_name(void);
 
+/* Diagnostic: voxels that the certified fast path handed to the exact per-voxel fallback
+ * on `device` since the last reset (see DESIGN.md "certified decisions"); -1 if unknown. */
+long long mpdaf_b200_slow_voxels(int device, int reset);
+
 /* Number of usable sm_100 devices (0 when none / no driver). */
 int mpdaf_b200_device_count(void);
 const char *mpdaf_b200_last_error(void);

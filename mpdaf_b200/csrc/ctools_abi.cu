@@ -20,6 +20,7 @@
 
 #include "../../include/mpdaf_b200.h"
 #include "combine_kernels.cuh"
+#include "sigclip_tile.cuh"
 #include "fits_reader.h"
 #include "synth_core.h"
 
@@ -55,6 +56,7 @@ struct DeviceState {
     int sm_count = 0;
     unsigned long long* counters = nullptr;  // [2][kGenericMax]: valid, select
     StackTable* table = nullptr;             // device copy for the generic kernels
+    unsigned long long* slow = nullptr;      // voxels recomputed by the exact fallback (diagnostic)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 DeviceState g_dev[16];
@@ -75,6 +77,8 @@ int device_ready(int device)
     d.sm_count = prop.multiProcessorCount;
     MB_CUDA(cudaMalloc(&d.counters, 2 * kGenericMax * sizeof(unsigned long long)));
     MB_CUDA(cudaMalloc(&d.table, sizeof(StackTable)));
+    MB_CUDA(cudaMalloc(&d.slow, sizeof(unsigned long long)));
+    MB_CUDA(cudaMemset(d.slow, 0, sizeof(unsigned long long)));
     MB_CUDA(cudaEventCreate(&d.ev0));
     MB_CUDA(cudaEventCreate(&d.ev1));
     d.ready = true;
@@ -149,6 +153,42 @@ int launch_reg(const Job& j, bool unit, int device, cudaStream_t stream)
     return launch_persistent(sigclip_reg_kernel<NB, false>, device, j.a.nvox, stream, s, j.a);
 }
 
+// Tile-staged sigma clip (sigclip_tile.cuh): the main kernel for float32 stacks up to 64 deep.
+template <int NB>
+int launch_tile(const Job& j, bool unit, int device, cudaStream_t stream)
+{
+    TileArgs<NB> s;
+    bool aligned = true;
+    for (int i = 0; i < NB; i++) {
+        const bool in = i < j.nfiles;
+        s.data[i] = in ? static_cast<const float*>(j.data[i]) : nullptr;
+        s.var[i] = (in && j.var) ? static_cast<const float*>(j.var[i]) : nullptr;
+        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
+        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
+        s.scale2[i] = s.scale[i] * s.scale[i];
+        if (in && (reinterpret_cast<uintptr_t>(s.data[i]) & 15u)) aligned = false;
+        if (in && s.var[i] && (reinterpret_cast<uintptr_t>(s.var[i]) & 15u)) aligned = false;
+    }
+    char name[64];
+    std::snprintf(name, sizeof name, "sigclip_tile<%d,%s,%s>", NB, unit ? "unit" : "scaled", aligned ? "tma" : "ldg");
+    g_last_kernel = name;
+    auto launch = [&](auto kernel) -> int {
+        const int smem = (int)sizeof(TileSmem<NB>);
+        MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long long ntiles = (j.a.nvox + kThreads - 1) / kThreads;
+        const int grid = (int)std::max(1LL, std::min(ntiles, (long long)g_dev[device].sm_count * per_sm));
+        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, aligned ? 1 : 0, g_dev[device].slow);
+        MB_CUDA(cudaGetLastError());
+        g_last_launches++;
+        return MPDAF_B200_OK;
+    };
+    if (unit) return launch(sigclip_tile_kernel<NB, true>);
+    return launch(sigclip_tile_kernel<NB, false>);
+}
+
 template <int MAXN, typename ElemT>
 int launch_generic(const Job& j, int device, cudaStream_t stream)
 {
@@ -185,6 +225,19 @@ int enqueue_combine(const Job& j, int device, cudaStream_t stream)
     }
     const int nb = bucket_of(j.nfiles);
     const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32 && (j.median || !j.a.mad);
+    static const bool use_v1 = std::getenv("MPDAF_B200_KERNEL") && std::string(std::getenv("MPDAF_B200_KERNEL")) == "reg";
+    if (reg_ok && !j.median && !use_v1) {
+        switch (nb) {
+            case 4: return launch_tile<4>(j, unit, device, stream);
+            case 8: return launch_tile<8>(j, unit, device, stream);
+            case 12: return launch_tile<12>(j, unit, device, stream);
+            case 16: return launch_tile<16>(j, unit, device, stream);
+            case 24: return launch_tile<24>(j, unit, device, stream);
+            case 32: return launch_tile<32>(j, unit, device, stream);
+            case 48: return launch_tile<48>(j, unit, device, stream);
+            case 64: return launch_tile<64>(j, unit, device, stream);
+        }
+    }
     if (reg_ok) {
         switch (nb) {
             case 4: return launch_reg<4>(j, unit, device, stream);
@@ -628,6 +681,16 @@ int mpdaf_b200_median_arrays(int nfiles, const void* const* data, int elem_type,
 }
 
 double mpdaf_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+
+long long mpdaf_b200_slow_voxels(int device, int reset)
+{
+    if (device < 0 || device >= 16 || !g_dev[device].ready) return -1;
+    unsigned long long v = 0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    if (cudaMemcpy(&v, g_dev[device].slow, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    if (reset) cudaMemset(g_dev[device].slow, 0, sizeof v);
+    return (long long)v;
+}
 int mpdaf_b200_last_launch_count(void) { return g_last_launches; }
 const char* mpdaf_b200_last_kernel_name(void) { return g_last_kernel.c_str(); }
 const char* mpdaf_b200_last_error(void) { return g_error.c_str(); }

@@ -61,6 +61,19 @@ KERNEL(k_dce, double a[CH]; double b[CH],
 KERNEL(k_fce, float a[CH]; float b[CH],
        a[c] = seedf + c; b[c] = seedf * c,
        asm volatile("{.reg .f32 t; min.f32 t, %0, %1; max.f32 %1, %0, %1; mov.f32 %0, t;}" : "+f"(a[c]), "+f"(b[c])), acc += (a[c] + b[c]))  // 1 f32 compare-exchange
+KERNEL(k_fce_addsub, float a[CH]; float b[CH],
+       a[c] = seedf + c; b[c] = seedf * c,
+       asm volatile("{.reg .f32 t; .reg .b32 x, y, z; min.f32 t, %0, %1; mov.b32 x, %0; mov.b32 y, %1; mov.b32 z, t; add.s32 x, x, y; sub.s32 x, x, z; mov.b32 %1, x; mov.f32 %0, t;}" : "+f"(a[c]), "+f"(b[c])), acc += (a[c] + b[c]))  // CE = FMNMX + integer a+b-lo
+KERNEL(k_shfl, int a[CH]; int b = seedi,
+       a[c] = seedi + c + threadIdx.x, asm volatile("{.reg .b32 t; shfl.sync.bfly.b32 t, %0, 1, 0x1f, 0xffffffff; xor.b32 %0, %0, t;}" : "+r"(a[c])), acc += a[c])  // SHFL + LOP
+KERNEL(k_popc, int a[CH]; int b = seedi,
+       a[c] = seedi + c, asm volatile("{.reg .b32 t; popc.b32 t, %0; add.s32 %0, %0, t;}" : "+r"(a[c])), acc += a[c])  // POPC + IADD
+KERNEL(k_cvt_up, float a[CH]; int r[CH],
+       a[c] = seedf + c; r[c] = c, asm volatile("{.reg .f64 t; .reg .b32 lo, hi; cvt.f64.f32 t, %1; mov.b64 {lo, hi}, t; xor.b32 %0, %0, hi;}" : "+r"(r[c]) : "f"(a[c])), acc += r[c])  // F2F.F64.F32 + LOP
+KERNEL(k_cvt_down, double a[CH]; int r[CH],
+       a[c] = seedd + c; r[c] = c, asm volatile("{.reg .f32 t; .reg .b32 u; cvt.rn.f32.f64 t, %1; mov.b32 u, t; xor.b32 %0, %0, u;}" : "+r"(r[c]) : "d"(a[c])), acc += r[c])  // F2F.F32.F64 + LOP
+KERNEL(k_lds, int a[CH]; __shared__ int sm[TPB * 4]; sm[threadIdx.x] = seedi; sm[threadIdx.x + TPB] = 0,
+       a[c] = threadIdx.x * 4, asm volatile("{.reg .b32 t; ld.shared.b32 t, [%0]; add.s32 %0, %0, t;}" : "+r"(a[c])), acc += a[c])  // LDS + IADD (dependent)
 KERNEL(k_f2f_up, float a[CH]; double d[CH],
        a[c] = seedf + c; d[c] = 0, asm volatile("{.reg .f64 t; cvt.f64.f32 t, %1; add.rn.f64 %0, %0, t;}" : "+d"(d[c]) : "f"(a[c])), acc += (float)d[c])  // 1 F2F + 1 DADD
 KERNEL(k_f2f_down, double a[CH]; float f[CH],
@@ -134,6 +147,12 @@ int main()
     run("dsetp+sel", k_dsetp_sel, 2);
     run("f64 cmpxchg", k_dce, 1);
     run("f32 cmpxchg", k_fce, 1);
+    run("f32 cmpxchg addsub", k_fce_addsub, 1);
+    run("shfl+lop", k_shfl, 2);
+    run("popc+iadd", k_popc, 2);
+    run("cvt.f64.f32+lop", k_cvt_up, 2);
+    run("cvt.f32.f64+lop", k_cvt_down, 2);
+    run("lds+iadd", k_lds, 2);
     run("f2f.f64.f32+dadd", k_f2f_up, 2);
     run("f2f.f32.f64+fadd", k_f2f_down, 2);
     run("fmnmx+dadd", k_mix_fmnmx_dadd, 2);
