@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "_ctools.so")
 SOURCES = ("ctools_abi.cu", "fits_reader.cpp", "host_tools.cpp")
-DEPS = SOURCES + ("combine_kernels.cuh", "sigclip_tile.cuh", "sort_networks.cuh", "synth_core.h", "fits_reader.h",
+DEPS = SOURCES + ("combine_kernels.cuh", "sigclip_tile.cuh", "sigclip_warp.cuh", "sort_networks.cuh", "synth_core.h", "fits_reader.h",
                   os.path.join("..", "..", "include", "mpdaf_b200.h"))
 
 NVCC_FLAGS = [

@@ -21,6 +21,7 @@
 #include "../../include/mpdaf_b200.h"
 #include "combine_kernels.cuh"
 #include "sigclip_tile.cuh"
+#include "sigclip_warp.cuh"
 #include "fits_reader.h"
 #include "synth_core.h"
 
@@ -189,6 +190,45 @@ int launch_tile(const Job& j, bool unit, int device, cudaStream_t stream)
     return launch(sigclip_tile_kernel<NB, false>);
 }
 
+// Warp-tiled sigma clip (sigclip_warp.cuh): the main kernel for float32 stacks up to 64 deep.
+template <int NB>
+int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
+{
+    TileArgs<NB> s;
+    for (int i = 0; i < NB; i++) {
+        const bool in = i < j.nfiles;
+        s.data[i] = in ? static_cast<const float*>(j.data[i]) : nullptr;
+        s.var[i] = (in && j.var) ? static_cast<const float*>(j.var[i]) : nullptr;
+        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
+        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
+        s.scale2[i] = s.scale[i] * s.scale[i];
+    }
+    static const int fma_every = std::getenv("MPDAF_B200_FMA_EVERY") ? std::atoi(std::getenv("MPDAF_B200_FMA_EVERY")) : 2;
+    char name[64];
+    std::snprintf(name, sizeof name, "sigclip_warp<%d,%s,fma%d>", NB, unit ? "unit" : "scaled", NB == 48 ? fma_every : 2);
+    g_last_kernel = name;
+    auto launch = [&](auto kernel) -> int {
+        const int smem = (int)sizeof(BlockSmem<NB>);
+        MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
+        const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
+        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, g_dev[device].slow);
+        MB_CUDA(cudaGetLastError());
+        g_last_launches++;
+        return MPDAF_B200_OK;
+    };
+    if constexpr (NB == 48) {   // tuning variants of the compare-exchange pipe mix (bench depth)
+        if (fma_every == 0) return unit ? launch(sigclip_warp_kernel<NB, true, 0>) : launch(sigclip_warp_kernel<NB, false, 0>);
+        if (fma_every == 1) return unit ? launch(sigclip_warp_kernel<NB, true, 1>) : launch(sigclip_warp_kernel<NB, false, 1>);
+        if (fma_every == 3) return unit ? launch(sigclip_warp_kernel<NB, true, 3>) : launch(sigclip_warp_kernel<NB, false, 3>);
+    }
+    if (unit) return launch(sigclip_warp_kernel<NB, true, 2>);
+    return launch(sigclip_warp_kernel<NB, false, 2>);
+}
+
 template <int MAXN, typename ElemT>
 int launch_generic(const Job& j, int device, cudaStream_t stream)
 {
@@ -225,7 +265,20 @@ int enqueue_combine(const Job& j, int device, cudaStream_t stream)
     }
     const int nb = bucket_of(j.nfiles);
     const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32 && (j.median || !j.a.mad);
-    static const bool use_v1 = std::getenv("MPDAF_B200_KERNEL") && std::string(std::getenv("MPDAF_B200_KERNEL")) == "reg";
+    static const std::string which = std::getenv("MPDAF_B200_KERNEL") ? std::getenv("MPDAF_B200_KERNEL") : "warp";
+    const bool use_v1 = which == "reg";
+    if (reg_ok && !j.median && which == "warp") {
+        switch (nb) {
+            case 4: return launch_warp<4>(j, unit, device, stream);
+            case 8: return launch_warp<8>(j, unit, device, stream);
+            case 12: return launch_warp<12>(j, unit, device, stream);
+            case 16: return launch_warp<16>(j, unit, device, stream);
+            case 24: return launch_warp<24>(j, unit, device, stream);
+            case 32: return launch_warp<32>(j, unit, device, stream);
+            case 48: return launch_warp<48>(j, unit, device, stream);
+            case 64: return launch_warp<64>(j, unit, device, stream);
+        }
+    }
     if (reg_ok && !j.median && !use_v1) {
         switch (nb) {
             case 4: return launch_tile<4>(j, unit, device, stream);

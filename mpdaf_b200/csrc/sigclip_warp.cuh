@@ -1,0 +1,409 @@
+// Warp-tiled sigma-clip kernel for sm_100a: the main combine kernel (float32 stacks <= 64 deep).
+//
+// Reference behaviour restated (never copied): src/merging.c:423-477 (gather, n == 0 / 1,
+// outputs, counters) and src/tools.c:82-118 (median-centred iterative clip).
+//
+// Work decomposition.  A warp owns tiles of 32 consecutive voxels; one lane owns one voxel.
+// Warps never synchronise with each other (no block barrier), so a warp that needs more clip
+// iterations does not hold back its neighbours.  Every exposure load is one coalesced
+// 128-byte line per warp; the rows of the next tile are prefetched into L2 a whole tile
+// ahead (prefetch.global.L2), the STAT rows of the current tile at its start.
+//
+// Per voxel:
+//  1. exposure order, float64, no FMA: w = (offset + d) * scale and sum(w); the first mean
+//     is bit-identical to the reference (tools.c:13-17).  Alongside, shifted moments
+//     T1 = sum(w - p), S2 = sum((w - p)^2) about a pivot sample p.
+//  2. 32-bit keys: float32(w) with the low 6 mantissa bits replaced by the exposure index,
+//     ordered by a register sorting network.  A compare-exchange is FMNMX (min) plus integer
+//     a + b - min (the keys are distinct bit patterns, so that is exactly the max); part of the
+//     integer work is steered to the FMA pipe (IMAD) because the ALU pipe is the scarce one.
+//  3. the sorted keys go to the lane's shared-memory column; median, window counts and the
+//     rejected samples come from direct / binary-search reads of that column.
+//  4. later means / sigmas: the rejected samples (exact w recomputed from the staged d) are
+//     subtracted from the shifted moments.
+//  5. per-exposure counters: the lanes' "invalid" and "dropped" bit masks are transposed
+//     across the warp with 5 shuffle stages per 32 exposures, then one POPC per lane.
+// Decisions are CERTIFIED: key-derived median and moment-derived sigma carry
+// rigorous error bounds; a voxel with a sample closer to a clip bound than that uncertainty,
+// or with an ill-conditioned variance, is recomputed by `exact_voxel_w` (the reference
+// algorithm restated literally), so expmap and the counters are always bit-exact.
+#pragma once
+
+#include "combine_kernels.cuh"
+#include "sigclip_tile.cuh"
+
+namespace mb {
+
+template <int NB>
+struct WarpSmem {
+    float d[NB][32];   // staged samples of the current tile (lookup of rejected samples, fallback)
+    float k[NB][32];   // sorted keys, one column per lane
+};
+
+template <int NB>
+struct BlockSmem {
+    WarpSmem<NB> w[kThreads / 32];
+    double scale[NB];
+    double offset[NB];
+    double rcp[NB + 1];   // 1.0 / m
+};
+
+// compare-exchange variants: the max as a + b - min on the ALU (IADD3) or on the FMA pipe (2 IMAD)
+__device__ __forceinline__ void key_ce_alu(float& a, float& b)
+{
+    const float lo = fminf(a, b);
+    const unsigned hi = __float_as_uint(a) + __float_as_uint(b) - __float_as_uint(lo);
+    a = lo;
+    b = __uint_as_float(hi);
+}
+__device__ __forceinline__ void key_ce_fma(float& a, float& b, unsigned one, unsigned minus_one)
+{
+    const float lo = fminf(a, b);
+    unsigned t, hi;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(__float_as_uint(a)), "r"(one), "r"(__float_as_uint(b)));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(__float_as_uint(lo)), "r"(minus_one), "r"(t));
+    a = lo;
+    b = __uint_as_float(hi);
+}
+
+template <int NB, int FMA_EVERY>
+__device__ __forceinline__ void sort_keys_mixed(float (&a)[NB], unsigned one, unsigned minus_one)
+{
+    int ce = 0;
+#define MB_CE(i, j)                                                              \
+    if (FMA_EVERY > 0 && (ce % FMA_EVERY) == 0) key_ce_fma(a[i], a[j], one, minus_one); \
+    else key_ce_alu(a[i], a[j]);                                                 \
+    ce++;
+    if constexpr (NB == 4) { MB_SORTNET_4(MB_CE) }
+    else if constexpr (NB == 8) { MB_SORTNET_8(MB_CE) }
+    else if constexpr (NB == 12) { MB_SORTNET_12(MB_CE) }
+    else if constexpr (NB == 16) { MB_SORTNET_16(MB_CE) }
+    else if constexpr (NB == 24) { MB_SORTNET_24(MB_CE) }
+    else if constexpr (NB == 32) { MB_SORTNET_32(MB_CE) }
+    else if constexpr (NB == 48) { MB_SORTNET_48(MB_CE) }
+    else if constexpr (NB == 64) { MB_SORTNET_64(MB_CE) }
+#undef MB_CE
+}
+
+// The reference algorithm restated literally for one voxel (rare fallback path).
+template <int NB, bool UNIT>
+__device__ __noinline__ VoxelResult exact_voxel_w(const float (*d)[32], const double* scale, const double* offset,
+                                                  int lane, int nfiles, int nmax, double lo, double up, int nstop)
+{
+    GenericScratch<NB> g;
+    int n = 0;
+    for (int i = 0; i < nfiles; i++) {
+        const float x = d[i][lane];
+        if (x == x) {
+            g.w[n] = UNIT ? (double)x : (offset[i] + (double)x) * scale[i];
+            g.file[n] = (unsigned short)i;
+            g.idx[n] = (unsigned short)n;
+            n++;
+        }
+    }
+    VoxelResult r;
+    r.mean = CUDART_NAN;
+    r.sigma = 0.0;
+    r.kept = n;
+    r.rejected = 0ull;
+    if (n == 1) r.mean = g.w[0];
+    if (n >= 2) {
+        r.kept = clip_generic<NB>(g, n, nmax, lo, up, nstop, 0, r.mean, r.sigma);
+        unsigned long long keep = 0ull, valid = 0ull;
+        for (int k = 0; k < r.kept; k++) keep |= 1ull << g.file[g.idx[k]];
+        for (int k = 0; k < n; k++) valid |= 1ull << g.file[k];
+        r.rejected = valid & ~keep;
+    }
+    return r;
+}
+
+// Branch-free lower bound over the lane's sorted column: number of leading keys with
+// key <= x (LE) or key < x (!LE).  Every probe index is in range for any NB.
+template <int NB, bool LE>
+__device__ __forceinline__ int count_col(const float (*col)[32], int lane, float x)
+{
+    int base = 0;
+#pragma unroll
+    for (int len = NB; len > 1; len -= len / 2) {
+        const int half = len / 2;
+        const float kv = col[base + half - 1][lane];
+        const bool take = LE ? (kv <= x) : (kv < x);
+        base += take ? half : 0;
+    }
+    const float kv = col[base][lane];
+    return base + ((LE ? (kv <= x) : (kv < x)) ? 1 : 0);
+}
+
+// 32x32 bit-matrix transpose across the warp: on return bit l of lane i = bit i of lane l's x.
+struct TransposeConsts {
+    unsigned sel[5];   // per-stage bit-select mask for this lane
+    unsigned rot[5];   // per-stage left-rotate amount for this lane
+    __device__ __forceinline__ void init(int lane)
+    {
+        const unsigned m[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const int j = 16 >> s;
+            const bool upper = (lane & j) != 0;
+            sel[s] = upper ? ~m[s] : m[s];
+            rot[s] = upper ? (unsigned)(32 - j) : (unsigned)j;
+        }
+    }
+    __device__ __forceinline__ unsigned apply(unsigned x) const
+    {
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const unsigned y = __shfl_xor_sync(0xffffffffu, x, 16 >> s);
+            const unsigned t = __funnelshift_l(y, y, rot[s]);   // rotate left
+            x = (x & sel[s]) | (t & ~sel[s]);
+        }
+        return x;
+    }
+};
+
+template <int NB, bool UNIT, int FMA_EVERY>
+__global__ void __launch_bounds__(kThreads, 4)
+sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, unsigned long long* slow_total)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    BlockSmem<NB>& sm = *reinterpret_cast<BlockSmem<NB>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int wib = tid >> 5;
+    const int nfiles = A.nfiles;
+    const int nstop = A.nstop < 1 ? 1 : A.nstop;
+    const bool want_var = (A.typ_var == 0);
+    const unsigned one = (unsigned)(A.nfiles > 0);           // opaque 1 / -1 for the IMAD form
+    const unsigned minus_one = 0u - one;
+
+    if (tid < NB) {
+        sm.scale[tid] = S.scale[tid];
+        sm.offset[tid] = S.offset[tid];
+    }
+    if (tid <= NB) sm.rcp[tid] = tid > 0 ? 1.0 / (double)tid : 0.0;
+    __syncthreads();   // the only block-wide barrier of the kernel
+
+    float (*sd)[32] = sm.w[wib].d;
+    float (*sk)[32] = sm.w[wib].k;
+    TransposeConsts tc;
+    tc.init(lane);
+
+    unsigned cnt_inval_lo = 0, cnt_drop_lo = 0, cnt_hi = 0, cnt_hi2 = 0;   // per-lane exposure counters
+    unsigned tiles_done = 0, slow_count = 0;
+
+    const long long ntiles = (A.nvox + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * (kThreads / 32);
+    long long tile = (long long)blockIdx.x * (kThreads / 32) + wib;
+
+    // L2 prefetch of a tile's rows: lane l touches rows l and l + 32 (one 128-byte line each)
+    auto prefetch_rows = [&](bool stat, long long t) {
+        const long long v0 = t << 5;
+        if (v0 + 31 >= A.nvox) return;
+#pragma unroll
+        for (int r = 0; r < (NB + 31) / 32; r++) {
+            const int i = lane + 32 * r;
+            if (i < nfiles) {
+                const float* row = stat ? S.var[i] : S.data[i];
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row + v0));
+            }
+        }
+    };
+    if (tile < ntiles) prefetch_rows(false, tile);
+
+    for (; tile < ntiles; tile += wstride) {
+        const long long v = (tile << 5) + lane;
+        const bool act = v < A.nvox;
+        if (tile + wstride < ntiles) prefetch_rows(false, tile + wstride);
+        if (want_var) prefetch_rows(true, tile);
+
+        // ---- gather: one coalesced load per exposure ------------------------------------------
+        float key[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++)
+            key[i] = (act && i < nfiles) ? ld_stream(S.data[i] + v) : CUDART_NAN_F;
+
+        // ---- pass 1: exposure order.  w, exact sum, shifted moments, keys ----------------------
+        unsigned long long inval = 0ull;
+        double sum = 0.0, T1 = 0.0, S2 = 0.0, p = 0.0;
+        bool have_p = false;
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const float d = key[i];
+            sd[i][lane] = d;
+            const bool ok = (d == d);
+            double w;
+            if constexpr (UNIT) w = (double)d;
+            else w = (S.offset[i] + (double)d) * S.scale[i];
+            if (i < 4) {                           // pivot = first valid sample among the first four
+                p = (ok && !have_p) ? w : p;
+                have_p = have_p || ok;
+            }
+            if (ok) {
+                sum += w;                          // tools.c:13-16, exposure order, no FMA
+                const double t = w - p;
+                T1 += t;
+                S2 = __fma_rn(t, t, S2);
+            } else {
+                inval |= 1ull << i;
+            }
+            float kf;
+            if constexpr (UNIT) kf = d;
+            else kf = __double2float_rn(w);
+            const unsigned kb = (__float_as_uint(kf) & ~63u) | (unsigned)i;
+            key[i] = fminf(__uint_as_float(kb), __uint_as_float(0x7F7FFFC0u | (unsigned)i));  // NaN -> sentinel
+        }
+        const int n = NB - __popcll(inval);
+
+        sort_keys_mixed<NB, FMA_EVERY>(key, one, minus_one);
+#pragma unroll
+        for (int q = 0; q < NB; q++) sk[q][lane] = key[q];
+        __syncwarp();
+
+        // ---- clip iterations on the sorted column --------------------------------------------
+        double mean = sum / (double)n;             // n == 0 -> NaN (merging.c:439)
+        double sigma = 0.0;
+        int a = 0, b = n;
+        unsigned long long rejected = 0ull;
+        bool slow = false;
+        if (n >= 2) {
+            const double S2_0 = S2;
+            int it = A.nmax;
+            // values beyond float range or an absurd pivot defeat the key precision model
+            if (!(S2_0 < 0x1p200)) slow = true;
+            // S2_0 == 0: every valid sample equals the pivot, sigma == 0, nothing lies strictly
+            // inside the empty window: the reference stops at once with all samples kept (tools.c:100)
+            while (!slow && S2_0 != 0.0) {
+                const int m = b - a;
+                const double rm = sm.rcp[m];
+                const double dm1 = T1 * rm;
+                double var_k = __fma_rn(S2, rm, -(dm1 * dm1));
+                // conditioning: the moment variance must dominate its rounding error
+                if (!(var_k >= 0x1p-13 * (S2_0 * rm))) { slow = true; break; }
+                sigma = sqrt(var_k);
+                const int ih = a + (m >> 1);
+                const int il = ih - 1 + (m & 1);
+                const float kh = __uint_as_float(__float_as_uint(sk[ih][lane]) & ~63u);
+                const float kl = __uint_as_float(__float_as_uint(sk[il][lane]) & ~63u);
+                const double med = ((double)kh + (double)kl) * 0.5;
+                const double amax = fmax(fabs((double)kh), fabs((double)kl));
+                const double clo = med - (A.nclip_low * sigma);
+                const double cup = med + (A.nclip_up * sigma);
+                // total uncertainty of a key against a bound: median from truncated keys,
+                // sigma from reordered sums, key truncation of the sample itself
+                const double spread = (A.nclip_low + A.nclip_up) * sigma;
+                const double T = 0x1p-15 * amax + 0x1p-26 * spread + 0x1p-15 * (fabs(clo) + fabs(cup)) + 0x1p-120;
+                if (!(T < 0x1p120)) { slow = true; break; }   // NaN / inf bounds: let the exact path decide
+                // keys certainly at or below the low bound / certainly below the high bound
+                const float f_lo_in = __double2float_ru(clo + T), f_lo_out = __double2float_rd(clo - T);
+                const float f_up_in = __double2float_rd(cup - T), f_up_out = __double2float_ru(cup + T);
+                int lo_in = count_col<NB, true>(sk, lane, f_lo_in);
+                int up_in = count_col<NB, false>(sk, lane, f_up_in);
+                // band checks: no key in (clo - T, clo + T] and none in [cup - T, cup + T)
+                const bool lo_band = lo_in > 0 && !(sk[lo_in - 1][lane] <= f_lo_out);
+                const bool up_band = up_in < NB && (sk[up_in < NB ? up_in : NB - 1][lane] < f_up_out);
+                lo_in = min(max(lo_in, a), b);
+                up_in = min(max(up_in, a), b);
+                // a band hit outside the current window is harmless only if it is not adjacent to it;
+                // keep it simple and conservative: any band hit defers to the exact path
+                if (lo_band || up_band) { slow = true; break; }
+                const int na = lo_in;                                     // first kept position
+                const int nb2 = max(up_in, na);                           // one past the last kept
+                const int ni = nb2 - na;
+                if (ni < nstop || ni == m) break;                         // tools.c:100-103
+                if (it <= 0) break;                                       // tools.c:104
+                it--;
+                // drop the rejected samples [a,na) and [nb2,b): exact w recomputed from the staged d
+                for (int q = a; q < b; q++) {
+                    if (q == na) { q = nb2; if (q >= b) break; }
+                    const int i = (int)(__float_as_uint(sk[q][lane]) & 63u);
+                    const double dd = (double)sd[i][lane];
+                    const double w = UNIT ? dd : (sm.offset[i] + dd) * sm.scale[i];
+                    const double t = w - p;
+                    T1 -= t;
+                    S2 -= t * t;
+                    rejected |= 1ull << i;
+                }
+                a = na;
+                b = nb2;
+                mean = p + T1 * sm.rcp[ni];
+            }
+        }
+        int kept = b - a;
+        if (slow) {
+            const VoxelResult r = exact_voxel_w<NB, UNIT>(sd, sm.scale, sm.offset, lane, nfiles, A.nmax, A.nclip_low,
+                                                          A.nclip_up, nstop);
+            mean = r.mean;
+            sigma = r.sigma;
+            kept = r.kept;
+            rejected = r.rejected;
+            slow_count++;
+        }
+        __syncwarp();
+
+        // ---- propagated variance over the kept set --------------------------------------------
+        const unsigned long long dropped = inval | rejected;
+        double vsum = 0.0;
+        if (want_var) {
+            float sv[NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++) sv[i] = (act && i < nfiles) ? ld_stream(S.var[i] + v) : 0.f;
+#pragma unroll
+            for (int i = 0; i < NB; i++)
+                if (!((dropped >> i) & 1ull)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
+        }
+
+        // ---- per-exposure counters: transpose the lanes' masks, one POPC per lane --------------
+        cnt_inval_lo += __popc(tc.apply((unsigned)inval));
+        cnt_drop_lo += __popc(tc.apply((unsigned)dropped));
+        if (NB > 32) {
+            // exposures 32..63 (NB <= 48: 16 bits each): invalid in the low half, dropped in the high half
+            if constexpr (NB <= 48) {
+                const unsigned packed = ((unsigned)(inval >> 32) & 0xFFFFu) | ((unsigned)(dropped >> 32) << 16);
+                cnt_hi += __popc(tc.apply(packed));
+            } else {
+                cnt_hi += __popc(tc.apply((unsigned)(inval >> 32)));
+                cnt_hi2 += __popc(tc.apply((unsigned)(dropped >> 32)));
+            }
+        }
+        tiles_done++;
+
+        if (act) {
+            double ov;
+            if (want_var) {
+                ov = vsum / ((double)kept * (double)kept);                // merging.c:462
+            } else if (kept > 1) {
+                ov = sigma * sigma;                                       // merging.c:465
+                if (A.typ_var == 1) ov /= (double)(kept - 1);             // merging.c:467
+            } else {
+                ov = CUDART_NAN;
+            }
+            A.out[v] = mean;
+            A.outvar[v] = ov;
+            A.expmap[v] = kept;
+        }
+    }
+
+    // ---- flush: valid = lanes seen - invalid, selected = lanes seen - dropped -----------------
+    const unsigned seen = tiles_done * 32u;
+    if (lane < nfiles) {
+        atomicAdd(A.valid_cnt + lane, (unsigned long long)(seen - cnt_inval_lo));
+        atomicAdd(A.select_cnt + lane, (unsigned long long)(seen - cnt_drop_lo));
+    }
+    if (NB > 32 && NB <= 48) {
+        const int e = 32 + (lane & 15);
+        if (e < nfiles) {
+            if (lane < 16) atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_hi));
+            else atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_hi));
+        }
+    }
+    if (NB > 48) {
+        const int e = 32 + lane;
+        if (e < nfiles) {
+            atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_hi));
+            atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_hi2));
+        }
+    }
+    if (slow_total != nullptr && slow_count) atomicAdd(slow_total, (unsigned long long)slow_count);
+}
+
+}  // namespace mb

@@ -33,26 +33,29 @@ def test_register_kernels_every_bucket(n, location):
             want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, **kw)
             got = cuda().combine_cuda(data, var, vartype=vartype, nclip=nclip, location=location, **kw)
             assert_same_result(got, want)
-            assert "reg" in cuda().kernel_name()
+            assert "warp" in cuda().kernel_name()
     want = oracle.median_port(data)
     got = cuda().median_cuda(data, location=location)
     assert_same_result(got, want, median=True)
 
 
 def test_unit_scale_path_is_bit_exact():
-    """Without scales/offsets the sums run in the reference's order: data identical to the bit."""
+    """Voxels without a rejection are identical to the bit (first mean in exposure order);
+    after a rejection the mean comes from shifted moments: <= 1e-12 relative."""
     rng = np.random.default_rng(5)
     data, var = random_stack(rng, 48, (5, 9, 10), nan_frac=0.05, outlier_frac=0.03)
     for nclip in (5.0, 3.0, 2.0):
         want = oracle.combine_port(data, var, nclip=nclip, vartype="stat_one")
         got = cuda().combine_cuda(data, var, nclip=nclip, vartype="stat_one")
         assert "unit" in cuda().kernel_name()
-        assert_same_result(got, want, exact_data=True)
-        np.testing.assert_array_equal(got["var"], want["var"])
+        assert_same_result(got, want, rtol=1e-12)
+        untouched = want["expmap"] == sum(~np.isnan(d.reshape(-1)) for d in data)
+        np.testing.assert_array_equal(got["data"][untouched], want["data"][untouched])
+        assert untouched.any() and (~untouched).any()
         assert (want["select_pix"] < want["valid_pix"]).any()
 
 
-def test_scaled_path_is_bit_exact_too():
+def test_scaled_path_first_mean_is_bit_exact():
     rng = np.random.default_rng(6)
     n = 24
     data, var = random_stack(rng, n, (5, 9, 10), nan_frac=0.05, outlier_frac=0.05)
@@ -61,7 +64,9 @@ def test_scaled_path_is_bit_exact_too():
     got = cuda().combine_cuda(data, var, scales=np.linspace(0.5, 2, n), offsets=np.linspace(-3, 3, n),
                               nclip=2.5, vartype="stat_mean")
     assert "scaled" in cuda().kernel_name()
-    assert_same_result(got, want, exact_data=True)
+    assert_same_result(got, want, rtol=1e-12)
+    untouched = want["expmap"] == sum(~np.isnan(d.reshape(-1)) for d in data)
+    np.testing.assert_array_equal(got["data"][untouched], want["data"][untouched])
 
 
 @pytest.mark.parametrize("nmax,lo,up,nstop", [(0, 2.0, 2.0, 2), (1, 1.5, 3.0, 1), (3, 1.0, 1.0, 3),
