@@ -203,30 +203,34 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
         s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
         s.scale2[i] = s.scale[i] * s.scale[i];
     }
-    static const int fma_every = std::getenv("MPDAF_B200_FMA_EVERY") ? std::atoi(std::getenv("MPDAF_B200_FMA_EVERY")) : 2;
     char name[64];
-    std::snprintf(name, sizeof name, "sigclip_warp<%d,%s,fma%d>", NB, unit ? "unit" : "scaled", NB == 48 ? fma_every : 2);
+    std::snprintf(name, sizeof name, "sigclip_warp<%d,%s>", NB, unit ? "unit" : "scaled");
     g_last_kernel = name;
-    auto launch = [&](auto kernel) -> int {
+    auto launch = [&](auto kernel, long long t0, long long t1) -> int {
+        if (t1 <= t0) return MPDAF_B200_OK;
         const int smem = (int)sizeof(BlockSmem<NB>);
         MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
         MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
         if (per_sm < 1) per_sm = 1;
-        const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
+        const long long nblocks = (t1 - t0 + (kThreads / 32) - 1) / (kThreads / 32);
         const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, g_dev[device].slow);
+        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, t0, t1, g_dev[device].slow);
         MB_CUDA(cudaGetLastError());
         g_last_launches++;
         return MPDAF_B200_OK;
     };
-    if constexpr (NB == 48) {   // tuning variants of the compare-exchange pipe mix (bench depth)
-        if (fma_every == 0) return unit ? launch(sigclip_warp_kernel<NB, true, 0>) : launch(sigclip_warp_kernel<NB, false, 0>);
-        if (fma_every == 1) return unit ? launch(sigclip_warp_kernel<NB, true, 1>) : launch(sigclip_warp_kernel<NB, false, 1>);
-        if (fma_every == 3) return unit ? launch(sigclip_warp_kernel<NB, true, 3>) : launch(sigclip_warp_kernel<NB, false, 3>);
+    const long long ntiles = (j.a.nvox + 31) / 32;
+    const long long full = (j.nfiles == NB) ? j.a.nvox / 32 : 0;   // tiles the fast variant may take
+    int rc;
+    if (unit) {
+        rc = launch(sigclip_warp_kernel<NB, true, 2, false>, 0, full);
+        if (rc == MPDAF_B200_OK) rc = launch(sigclip_warp_kernel<NB, true, 2, true>, full, ntiles);
+    } else {
+        rc = launch(sigclip_warp_kernel<NB, false, 2, false>, 0, full);
+        if (rc == MPDAF_B200_OK) rc = launch(sigclip_warp_kernel<NB, false, 2, true>, full, ntiles);
     }
-    if (unit) return launch(sigclip_warp_kernel<NB, true, 2>);
-    return launch(sigclip_warp_kernel<NB, false, 2>);
+    return rc;
 }
 
 template <int MAXN, typename ElemT>
