@@ -221,16 +221,8 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
         return MPDAF_B200_OK;
     };
     const long long ntiles = (j.a.nvox + 31) / 32;
-    const long long full = (j.nfiles == NB) ? j.a.nvox / 32 : 0;   // tiles the fast variant may take
-    int rc;
-    if (unit) {
-        rc = launch(sigclip_warp_kernel<NB, true, 2, false>, 0, full);
-        if (rc == MPDAF_B200_OK) rc = launch(sigclip_warp_kernel<NB, true, 2, true>, full, ntiles);
-    } else {
-        rc = launch(sigclip_warp_kernel<NB, false, 2, false>, 0, full);
-        if (rc == MPDAF_B200_OK) rc = launch(sigclip_warp_kernel<NB, false, 2, true>, full, ntiles);
-    }
-    return rc;
+    if (unit) return launch(sigclip_warp_kernel<NB, true, 2>, 0, ntiles);
+    return launch(sigclip_warp_kernel<NB, false, 2>, 0, ntiles);
 }
 
 template <int MAXN, typename ElemT>

@@ -161,11 +161,7 @@ struct TransposeConsts {
     }
 };
 
-// SAFE = false: every exposure slot is in use (nfiles == NB) and every tile is full, so the
-// gather is unconditional and pass 1 is the predicated PTX sequence below.  SAFE = true also
-// handles nfiles < NB and the ragged last tile (per-row / per-lane selects).  The host runs
-// the fast variant on the full tiles and the safe one on what is left.
-template <int NB, bool UNIT, int FMA_EVERY, bool SAFE>
+template <int NB, bool UNIT, int FMA_EVERY>
 __global__ void __launch_bounds__(kThreads, 4)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
                     unsigned long long* slow_total)
@@ -225,138 +221,42 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         float key[NB];
 #pragma unroll
         for (int i = 0; i < NB; i++) {
-            if constexpr (SAFE) {
-                key[i] = CUDART_NAN_F;
-                if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
-            } else {
-                asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
-            }
+            // predicated loads: ptxas keeps them batched at the top of the tile (unconditional
+            // ones get sunk next to their first use and their latency serialises)
+            key[i] = CUDART_NAN_F;
+            if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
         }
         asm volatile("" ::: "memory");
 
         // ---- pass 1: exposure order.  w, exact sum, shifted moments, keys ----------------------
         unsigned long long inval = 0ull;
         double sum = 0.0, T1 = 0.0, S2 = 0.0, p = 0.0;
-        if constexpr (SAFE) {
-            bool have_p = false;
+        bool have_p = false;
 #pragma unroll
-            for (int i = 0; i < NB; i++) {
-                const float d = key[i];
-                sd[i][lane] = d;
-                const bool ok = (d == d);
-                double w;
-                if constexpr (UNIT) w = (double)d;
-                else w = (S.offset[i] + (double)d) * S.scale[i];
-                if (i < 4) {                       // pivot = first valid sample among the first four
-                    p = (ok && !have_p) ? w : p;
-                    have_p = have_p || ok;
-                }
-                if (ok) {
-                    sum += w;                      // tools.c:13-16, exposure order, no FMA
-                    const double t = w - p;
-                    T1 += t;
-                    S2 = __fma_rn(t, t, S2);
-                } else {
-                    inval |= 1ull << i;
-                }
-                float kf;
-                if constexpr (UNIT) kf = d;
-                else kf = __double2float_rn(w);
-                const unsigned kb = (__float_as_uint(kf) & ~63u) | (unsigned)i;
-                key[i] = fminf(__uint_as_float(kb), __uint_as_float(0x7F7FFFC0u | (unsigned)i));  // NaN -> sentinel
+        for (int i = 0; i < NB; i++) {
+            const float d = key[i];
+            sd[i][lane] = d;
+            const bool ok = (d == d);
+            double w;
+            if constexpr (UNIT) w = (double)d;
+            else w = (S.offset[i] + (double)d) * S.scale[i];
+            if (i < 4) {                       // pivot = first valid sample among the first four
+                p = (ok && !have_p) ? w : p;
+                have_p = have_p || ok;
             }
-        } else {
-            // pivot = first valid sample among the first four
-            {
-                bool have_p = false;
-#pragma unroll
-                for (int i = 0; i < (NB < 4 ? NB : 4); i++) {
-                    const float d = key[i];
-                    const bool ok = (d == d);
-                    const double w = UNIT ? (double)d : (S.offset[i] + (double)d) * S.scale[i];
-                    p = (ok && !have_p) ? w : p;
-                    have_p = have_p || ok;
-                }
+            if (ok) {
+                sum += w;                      // tools.c:13-16, exposure order, no FMA
+                const double t = w - p;
+                T1 += t;
+                S2 = __fma_rn(t, t, S2);
+            } else {
+                inval |= 1ull << i;
             }
-            unsigned inv_lo = 0u, inv_hi = 0u;
-            // same arithmetic as the SAFE branch, spelled in PTX so that it stays predicated
-            // (the compiler otherwise branches around every `if (ok)` block)
-#pragma unroll
-            for (int i = 0; i < NB; i++) {
-                const float d = key[i];
-                sd[i][lane] = d;
-                const unsigned bit = 1u << (i & 31);
-                const float sentinel = __uint_as_float(0x7F7FFFC0u | (unsigned)i);
-                float kout;
-                if constexpr (UNIT) {
-                    if (i < 32)
-                        asm("{\n\t.reg .pred q;\n\t.reg .f64 w, t;\n\t.reg .b32 kb;\n\t"
-                            "setp.eq.f32 q, %5, %5;\n\t"
-                            "cvt.f64.f32 w, %5;\n\t"
-                            "@q add.rn.f64 %0, %0, w;\n\t"
-                            "sub.rn.f64 t, w, %6;\n\t"
-                            "@q add.rn.f64 %1, %1, t;\n\t"
-                            "@q fma.rn.f64 %2, t, t, %2;\n\t"
-                            "@!q or.b32 %3, %3, %7;\n\t"
-                            "mov.b32 kb, %5;\n\t"
-                            "lop3.b32 kb, kb, 0xFFFFFFC0, %8, 0xEA;\n\t"
-                            "mov.b32 %4, kb;\n\t}"
-                            : "+d"(sum), "+d"(T1), "+d"(S2), "+r"(inv_lo), "=f"(kout)
-                            : "f"(d), "d"(p), "r"(bit), "r"(i));
-                    else
-                        asm("{\n\t.reg .pred q;\n\t.reg .f64 w, t;\n\t.reg .b32 kb;\n\t"
-                            "setp.eq.f32 q, %5, %5;\n\t"
-                            "cvt.f64.f32 w, %5;\n\t"
-                            "@q add.rn.f64 %0, %0, w;\n\t"
-                            "sub.rn.f64 t, w, %6;\n\t"
-                            "@q add.rn.f64 %1, %1, t;\n\t"
-                            "@q fma.rn.f64 %2, t, t, %2;\n\t"
-                            "@!q or.b32 %3, %3, %7;\n\t"
-                            "mov.b32 kb, %5;\n\t"
-                            "lop3.b32 kb, kb, 0xFFFFFFC0, %8, 0xEA;\n\t"
-                            "mov.b32 %4, kb;\n\t}"
-                            : "+d"(sum), "+d"(T1), "+d"(S2), "+r"(inv_hi), "=f"(kout)
-                            : "f"(d), "d"(p), "r"(bit), "r"(i));
-                } else {
-                    const double off = S.offset[i], sc = S.scale[i];
-                    if (i < 32)
-                        asm("{\n\t.reg .pred q;\n\t.reg .f64 w, t;\n\t.reg .f32 kf;\n\t.reg .b32 kb;\n\t"
-                            "setp.eq.f32 q, %5, %5;\n\t"
-                            "cvt.f64.f32 w, %5;\n\t"
-                            "add.rn.f64 w, %9, w;\n\t"
-                            "mul.rn.f64 w, w, %10;\n\t"
-                            "@q add.rn.f64 %0, %0, w;\n\t"
-                            "sub.rn.f64 t, w, %6;\n\t"
-                            "@q add.rn.f64 %1, %1, t;\n\t"
-                            "@q fma.rn.f64 %2, t, t, %2;\n\t"
-                            "@!q or.b32 %3, %3, %7;\n\t"
-                            "cvt.rn.f32.f64 kf, w;\n\t"
-                            "mov.b32 kb, kf;\n\t"
-                            "lop3.b32 kb, kb, 0xFFFFFFC0, %8, 0xEA;\n\t"
-                            "mov.b32 %4, kb;\n\t}"
-                            : "+d"(sum), "+d"(T1), "+d"(S2), "+r"(inv_lo), "=f"(kout)
-                            : "f"(d), "d"(p), "r"(bit), "r"(i), "d"(off), "d"(sc));
-                    else
-                        asm("{\n\t.reg .pred q;\n\t.reg .f64 w, t;\n\t.reg .f32 kf;\n\t.reg .b32 kb;\n\t"
-                            "setp.eq.f32 q, %5, %5;\n\t"
-                            "cvt.f64.f32 w, %5;\n\t"
-                            "add.rn.f64 w, %9, w;\n\t"
-                            "mul.rn.f64 w, w, %10;\n\t"
-                            "@q add.rn.f64 %0, %0, w;\n\t"
-                            "sub.rn.f64 t, w, %6;\n\t"
-                            "@q add.rn.f64 %1, %1, t;\n\t"
-                            "@q fma.rn.f64 %2, t, t, %2;\n\t"
-                            "@!q or.b32 %3, %3, %7;\n\t"
-                            "cvt.rn.f32.f64 kf, w;\n\t"
-                            "mov.b32 kb, kf;\n\t"
-                            "lop3.b32 kb, kb, 0xFFFFFFC0, %8, 0xEA;\n\t"
-                            "mov.b32 %4, kb;\n\t}"
-                            : "+d"(sum), "+d"(T1), "+d"(S2), "+r"(inv_hi), "=f"(kout)
-                            : "f"(d), "d"(p), "r"(bit), "r"(i), "d"(off), "d"(sc));
-                }
-                key[i] = fminf(kout, sentinel);   // NaN -> sentinel
-            }
-            inval = ((unsigned long long)inv_hi << 32) | inv_lo;
+            float kf;
+            if constexpr (UNIT) kf = d;
+            else kf = __double2float_rn(w);
+            const unsigned kb = (__float_as_uint(kf) & ~63u) | (unsigned)i;
+            key[i] = fminf(__uint_as_float(kb), __uint_as_float(0x7F7FFFC0u | (unsigned)i));  // NaN -> sentinel
         }
         const int n = NB - __popcll(inval);
 
@@ -369,10 +269,10 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         // row 0 and idle lanes re-read the last voxel (both are masked out by `dropped`).
         float sv[NB];
         if (want_var) {
-            const long long vs = (SAFE && !act) ? A.nvox - 1 : v;
+            const long long vs = act ? v : A.nvox - 1;
 #pragma unroll
             for (int i = 0; i < NB; i++)
-                asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[(!SAFE || i < nfiles) ? i : 0] + vs));
+                asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
         }
 
         // ---- clip iterations on the sorted column --------------------------------------------
