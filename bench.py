@@ -272,6 +272,7 @@ def run_b200_arm(args):
     for _ in range(args.warmup):
         step(timed=False)
     torch.cuda.synchronize(dev)
+    ctools.mpdaf_b200_slow_voxels(local, 1)
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -394,6 +395,7 @@ def run_b200_arm(args):
         "clocks": clocks,
         "parity": parity,
         "rejected_fraction": float(1.0 - n_sel / max(1, int(valid.astype(np.int64).sum()))),
+        "exact_fallback_voxels": int(ctools.mpdaf_b200_slow_voxels(local, 0)),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

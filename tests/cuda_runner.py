@@ -100,3 +100,8 @@ def median_cuda(data, location="device", device=0):
 
 def kernel_name():
     return ctools.mpdaf_b200_last_kernel_name().decode()
+
+
+def slow_voxels(reset=True, device=0):
+    """Voxels the certified fast path handed to the exact fallback since the last reset."""
+    return int(ctools.mpdaf_b200_slow_voxels(device, 1 if reset else 0))

@@ -180,3 +180,87 @@ def test_dropin_file_symbols_against_reference(tmp_path, vartype, mad):
     rc = ctools.mpdaf_merging_median(ctypes.c_char_p(names), out, expmap, val)
     assert rc == 0
     assert_same_result(dict(data=out, expmap=expmap, valid_pix=val), wantm, median=True)
+
+
+# ---- certified decisions: the exact fallback must catch everything the bounds cannot prove -------
+
+def test_bench_like_data_needs_no_fallback():
+    from mpdaf_b200 import synth
+    data, var = synth.host_stack(48, (3, 40, 50), seed=1)
+    c = cuda()
+    c.slow_voxels()
+    kw = dict(scales=synth.default_scales(48), offsets=synth.default_offsets(48))
+    got = c.combine_cuda(data, var, **kw)
+    assert_same_result(got, oracle.combine_port(data, var, **kw))
+    assert c.slow_voxels() == 0
+    assert (got["select_pix"] < got["valid_pix"]).any()
+
+
+@pytest.mark.parametrize("n", [6, 16, 48])
+def test_quantised_data_with_bounds_on_samples(n):
+    """Small integers, heavy ties, clip bounds that land exactly on sample values: the band test
+    fires and the exact path must reproduce the reference's strict inequalities."""
+    rng = np.random.default_rng(n)
+    shape = (4, 16, 16)
+    data = [rng.integers(0, 4, size=shape).astype(np.float32) for _ in range(n)]
+    for d in data:
+        d[rng.random(shape) < 0.05] = np.nan
+        d[rng.random(shape) < 0.03] += 8
+    var = [np.ones(shape, dtype=np.float32) for _ in range(n)]
+    c = cuda()
+    c.slow_voxels()
+    total = 0
+    for nclip in (1.0, 2.0, (1.0, 2.0), 0.5):
+        for vartype in ("propagate", "stat_one"):
+            want = oracle.combine_port(data, var, nclip=nclip, vartype=vartype, nmax=3)
+            got = c.combine_cuda(data, var, nclip=nclip, vartype=vartype, nmax=3)
+            assert_same_result(got, want)
+        total += c.slow_voxels()
+    assert total > 0
+
+
+def test_ill_conditioned_and_extreme_values():
+    rng = np.random.default_rng(3)
+    shape = (2, 12, 12)
+    n = 12
+    c = cuda()
+    # mean >> sigma: relative spread 1e-6 (the moment variance cannot be trusted)
+    data = [(1.0e6 + rng.standard_normal(shape)).astype(np.float32) for _ in range(n)]
+    var = [np.ones(shape, dtype=np.float32)] * n
+    assert_same_result(c.combine_cuda(data, var, nclip=2.0), oracle.combine_port(data, var, nclip=2.0))
+    # the pivot (first exposure) is a gross outlier
+    data = [(10 + rng.standard_normal(shape)).astype(np.float32) for _ in range(n)]
+    data[0] = data[0] + np.float32(1.0e7)
+    assert_same_result(c.combine_cuda(data, var, nclip=3.0, vartype="stat_mean"),
+                       oracle.combine_port(data, var, nclip=3.0, vartype="stat_mean"))
+    # scaled values beyond the float32 range (keys saturate)
+    scales = np.full(n, 1.0e35)
+    data = [(1.0e4 * (1 + 0.1 * rng.standard_normal(shape))).astype(np.float32) for _ in range(n)]
+    data[3][0, 0, :] = -3.0e4
+    assert_same_result(c.combine_cuda(data, var, scales=scales, nclip=2.0, vartype="stat_one"),
+                       oracle.combine_port(data, var, scales=scales, nclip=2.0, vartype="stat_one"))
+    # denormal-range values and exact zeros
+    data = [(1.0e-42 * rng.integers(-5, 6, size=shape)).astype(np.float32) for _ in range(n)]
+    assert_same_result(c.combine_cuda(data, var, nclip=1.5, vartype="stat_one"),
+                       oracle.combine_port(data, var, nclip=1.5, vartype="stat_one"))
+    # every sample identical except one: sigma of the survivors is exactly 0 after the first clip
+    data = [np.full(shape, 5.0, dtype=np.float32) for _ in range(n)]
+    data[7][:] = 100.0
+    assert_same_result(c.combine_cuda(data, var, nclip=2.0, vartype="stat_one"),
+                       oracle.combine_port(data, var, nclip=2.0, vartype="stat_one"), exact_data=True)
+
+
+def test_random_fuzz_against_oracle():
+    """Many small random configurations (depth, NaN rate, outliers, parameters, scales)."""
+    rng = np.random.default_rng(2025)
+    c = cuda()
+    for trial in range(40):
+        n = int(rng.integers(2, 65))
+        shape = (2, int(rng.integers(3, 9)), int(rng.integers(3, 40)))
+        data, var = random_stack(rng, n, shape, nan_frac=float(rng.uniform(0, 0.4)),
+                                 outlier_frac=float(rng.uniform(0, 0.15)), ties=bool(trial % 5 == 0))
+        kw = dict(nmax=int(rng.integers(0, 5)), nclip=(float(rng.uniform(0.8, 5)), float(rng.uniform(0.8, 5))),
+                  nstop=int(rng.integers(1, 5)), vartype=["propagate", "stat_mean", "stat_one"][trial % 3])
+        if trial % 2:
+            kw.update(scales=rng.uniform(0.5, 2.0, n), offsets=rng.uniform(-2, 2, n))
+        assert_same_result(c.combine_cuda(data, var, **kw), oracle.combine_port(data, var, **kw))
