@@ -215,7 +215,8 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
         if (per_sm < 1) per_sm = 1;
         const long long nblocks = (t1 - t0 + (kThreads / 32) - 1) / (kThreads / 32);
         const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, t0, t1, g_dev[device].slow);
+        static const int phase_lock = std::getenv("MPDAF_B200_PHASE_LOCK") ? std::atoi(std::getenv("MPDAF_B200_PHASE_LOCK")) : 0;
+        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, t0, t1, phase_lock, g_dev[device].slow);
         MB_CUDA(cudaGetLastError());
         g_last_launches++;
         return MPDAF_B200_OK;
@@ -331,7 +332,47 @@ struct Slot {
     StackTable* d_table = nullptr;
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     bool timed = false;
+    size_t in_bytes = 0, chunk_cap = 0, host_bytes = 0;   // current capacities
 };
+
+// The staging slots are kept per device between calls (allocation, pinning and stream creation
+// cost more than a whole small combine); they only ever grow.
+constexpr int kSlots = 3;
+Slot g_slots[16][kSlots];
+
+int ensure_slot(Slot& s, size_t in_bytes, size_t chunk, bool host_staging)
+{
+    if (!s.stream) {
+        MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaMalloc(&s.d_table, sizeof(StackTable)));
+        MB_CUDA(cudaEventCreate(&s.k0));
+        MB_CUDA(cudaEventCreate(&s.k1));
+    }
+    if (in_bytes > s.in_bytes) {
+        cudaFree(s.d_in);
+        s.in_bytes = 0;
+        MB_CUDA(cudaMalloc(&s.d_in, in_bytes));
+        s.in_bytes = in_bytes;
+    }
+    if (chunk > s.chunk_cap) {
+        cudaFree(s.d_out);
+        cudaFree(s.d_var);
+        cudaFree(s.d_exp);
+        s.chunk_cap = 0;
+        MB_CUDA(cudaMalloc(&s.d_out, chunk * sizeof(double)));
+        MB_CUDA(cudaMalloc(&s.d_var, chunk * sizeof(double)));
+        MB_CUDA(cudaMalloc(&s.d_exp, chunk * sizeof(int)));
+        s.chunk_cap = chunk;
+    }
+    if (host_staging && in_bytes > s.host_bytes) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        s.host_bytes = 0;
+        MB_CUDA(cudaMallocHost(&s.h_in, in_bytes));
+        s.host_bytes = in_bytes;
+    }
+    s.timed = false;
+    return MPDAF_B200_OK;
+}
 
 struct SlabSource {
     // exactly one of the two is used
@@ -340,23 +381,6 @@ struct SlabSource {
     std::vector<mbfits::ImageHdu>* fits_data = nullptr;
     std::vector<mbfits::ImageHdu>* fits_var = nullptr;
 };
-
-void release_slots(std::vector<Slot>& slots)
-{
-    for (Slot& s : slots) {
-        if (s.stream) cudaStreamSynchronize(s.stream);
-        cudaFree(s.d_in);
-        cudaFree(s.d_out);
-        cudaFree(s.d_var);
-        cudaFree(s.d_exp);
-        cudaFree(s.d_table);
-        if (s.h_in) cudaFreeHost(s.h_in);
-        if (s.k0) cudaEventDestroy(s.k0);
-        if (s.k1) cudaEventDestroy(s.k1);
-        if (s.stream) cudaStreamDestroy(s.stream);
-    }
-    slots.clear();
-}
 
 long long env_ll(const char* name, long long dflt)
 {
@@ -374,25 +398,20 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     const long long nvox = job.a.nvox;
     const bool from_files = src.fits_data != nullptr;
 
-    // chunk: bounded staging (default 768 MiB of samples per slot), multiple of 1024 voxels
-    const long long budget = env_ll("MPDAF_B200_SLAB_BYTES", 768LL << 20);
+    // chunk: bounded staging per slot (default 128 MiB of samples: small enough that the copy
+    // of one chunk overlaps the kernel of the previous one even for short stacks, large enough
+    // that every per-exposure segment is a ~MB-sized copy), multiple of 1024 voxels
+    const long long budget = env_ll("MPDAF_B200_SLAB_BYTES", 128LL << 20);
     long long chunk = budget / ((long long)planes * esz);
     chunk = std::max(1024LL, chunk / 1024 * 1024);
     chunk = std::min(chunk, (nvox + 1023) / 1024 * 1024);
     if (chunk < 1) chunk = 1024;
-    const int nslots = (int)std::min<long long>(3, (nvox + chunk - 1) / chunk);
+    const int nslots = (int)std::max<long long>(1, std::min<long long>(kSlots, (nvox + chunk - 1) / chunk));
 
-    std::vector<Slot> slots(std::max(nslots, 1));
-    for (Slot& s : slots) {
-        MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        MB_CUDA(cudaMalloc(&s.d_in, (size_t)planes * chunk * esz));
-        MB_CUDA(cudaMalloc(&s.d_out, (size_t)chunk * sizeof(double)));
-        if (!job.median) MB_CUDA(cudaMalloc(&s.d_var, (size_t)chunk * sizeof(double)));
-        MB_CUDA(cudaMalloc(&s.d_exp, (size_t)chunk * sizeof(int)));
-        MB_CUDA(cudaMalloc(&s.d_table, sizeof(StackTable)));
-        if (from_files) MB_CUDA(cudaMallocHost(&s.h_in, (size_t)planes * chunk * esz));
-        MB_CUDA(cudaEventCreate(&s.k0));
-        MB_CUDA(cudaEventCreate(&s.k1));
+    Slot* slots = g_slots[device];
+    for (int k = 0; k < nslots; k++) {
+        const int rc0 = ensure_slot(slots[k], (size_t)planes * chunk * esz, (size_t)chunk, from_files);
+        if (rc0 != MPDAF_B200_OK) return rc0;
     }
 
     int rc = MPDAF_B200_OK;
@@ -400,7 +419,7 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     std::vector<const void*> dptr(planes);
     long long c = 0;
     for (long long v0 = 0; v0 < nvox && rc == MPDAF_B200_OK; v0 += chunk, c++) {
-        Slot& s = slots[c % slots.size()];
+        Slot& s = slots[c % nslots];
         const long long cnt = std::min(chunk, nvox - v0);
         // the slot's previous chunk must have left the device (and its pinned staging)
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { rc = fail(MPDAF_B200_ERR_CUDA, "slab stream failed"); break; }
@@ -475,17 +494,18 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         ok = ok && cudaMemcpyAsync(expmap + v0, s.d_exp, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
         if (!ok) rc = fail(MPDAF_B200_ERR_CUDA, "D2H of a result slab failed");
     }
-    for (Slot& s : slots) {
+    for (int k = 0; k < nslots; k++) {
+        Slot& s = slots[k];
         if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc == MPDAF_B200_OK)
             rc = fail(MPDAF_B200_ERR_CUDA, std::string("slab pipeline: ") + cudaGetErrorString(cudaGetLastError()));
         if (s.timed) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, s.k0, s.k1);
             kernel_ms += ms;
+            s.timed = false;
         }
     }
     g_last_kernel_ms = kernel_ms;
-    release_slots(slots);
     return rc;
 }
 

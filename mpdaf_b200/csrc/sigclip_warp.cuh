@@ -164,7 +164,7 @@ struct TransposeConsts {
 template <int NB, bool UNIT, int FMA_EVERY>
 __global__ void __launch_bounds__(kThreads, 4)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
-                    unsigned long long* slow_total)
+                    const int phase_lock, unsigned long long* slow_total)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockSmem<NB>& sm = *reinterpret_cast<BlockSmem<NB>*>(smem_raw);
@@ -194,7 +194,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 
     const long long ntiles = tile_end;
     const long long wstride = (long long)gridDim.x * (kThreads / 32);
-    long long tile = tile_begin + (long long)blockIdx.x * (kThreads / 32) + wib;
+    long long tile0 = tile_begin + (long long)blockIdx.x * (kThreads / 32);
 
     // L2 prefetch of a tile's rows: lane l touches rows l and l + 32 (one 128-byte line each)
     auto prefetch_rows = [&](bool stat, long long t) {
@@ -209,11 +209,17 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             }
         }
     };
-    if (tile < ntiles) prefetch_rows(false, tile);
+    if (tile0 + wib < ntiles) prefetch_rows(false, tile0 + wib);
 
-    for (; tile < ntiles; tile += wstride) {
+    // The trip count is uniform per block so that the optional per-tile barrier is legal; a warp
+    // whose last tile lies beyond the range runs it with every lane idle.
+    for (; tile0 < ntiles; tile0 += wstride) {
+        // phase lock: the four warps of a block start every tile together, so they walk the
+        // (large, unrolled) instruction stream nearly in step and share instruction-cache lines
+        if (phase_lock) __syncthreads();
+        const long long tile = tile0 + wib;
         const long long v = (tile << 5) + lane;
-        const bool act = v < A.nvox;
+        const bool act = tile < ntiles && v < A.nvox;
         if (tile + wstride < ntiles) prefetch_rows(false, tile + wstride);
         if (want_var) prefetch_rows(true, tile);
 
