@@ -226,6 +226,31 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
     return launch(sigclip_warp_kernel<NB, false, 2>, 0, ntiles);
 }
 
+template <int NB>
+int launch_median_warp(const Job& j, int device, cudaStream_t stream)
+{
+    TileArgs<NB> s;
+    for (int i = 0; i < NB; i++) {
+        s.data[i] = i < j.nfiles ? static_cast<const float*>(j.data[i]) : nullptr;
+        s.var[i] = nullptr;
+        s.scale[i] = 1.0;
+        s.offset[i] = 0.0;
+        s.scale2[i] = 1.0;
+    }
+    char name[64];
+    std::snprintf(name, sizeof name, "median_warp<%d>", NB);
+    g_last_kernel = name;
+    int per_sm = 0;
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, median_warp_kernel<NB>, kThreads, 0));
+    if (per_sm < 1) per_sm = 1;
+    const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
+    const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
+    median_warp_kernel<NB><<<grid, kThreads, 0, stream>>>(s, j.a);
+    MB_CUDA(cudaGetLastError());
+    g_last_launches++;
+    return MPDAF_B200_OK;
+}
+
 template <int MAXN, typename ElemT>
 int launch_generic(const Job& j, int device, cudaStream_t stream)
 {
@@ -274,6 +299,18 @@ int enqueue_combine(const Job& j, int device, cudaStream_t stream)
             case 32: return launch_warp<32>(j, unit, device, stream);
             case 48: return launch_warp<48>(j, unit, device, stream);
             case 64: return launch_warp<64>(j, unit, device, stream);
+        }
+    }
+    if (reg_ok && j.median && which == "warp") {
+        switch (nb) {
+            case 4: return launch_median_warp<4>(j, device, stream);
+            case 8: return launch_median_warp<8>(j, device, stream);
+            case 12: return launch_median_warp<12>(j, device, stream);
+            case 16: return launch_median_warp<16>(j, device, stream);
+            case 24: return launch_median_warp<24>(j, device, stream);
+            case 32: return launch_median_warp<32>(j, device, stream);
+            case 48: return launch_median_warp<48>(j, device, stream);
+            case 64: return launch_median_warp<64>(j, device, stream);
         }
     }
     if (reg_ok && !j.median && !use_v1) {

@@ -426,3 +426,85 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 }
 
 }  // namespace mb
+
+namespace mb {
+
+// ---------------------------------------------------------------------------------------------
+// Median (merging.c:232-253, tools.c:39-51), float32 stacks <= 64 deep.
+//
+// One lane owns one voxel.  Invalid samples (NaN, unused slots) are replaced alternately by
+// -inf and +inf, so that the valid samples stay centred in the sorted stack: the median of the
+// n valid samples is then always at the two fixed middle slots NB/2-1 and NB/2 (odd n: slot
+// NB/2-1 alone), and no data-dependent selection is needed.  The network's compare-exchange is
+// FMNMX + integer a+b-min with the integer part on the FMA pipe (the ALU pipe is the bottleneck
+// of this kernel); per-exposure valid counts come from one 32x32 bit transpose per 32 exposures.
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A)
+{
+    const int lane = threadIdx.x & 31;
+    const int nfiles = A.nfiles;
+    const unsigned one = (unsigned)(A.nfiles > 0);
+    const unsigned minus_one = 0u - one;
+    TransposeConsts tc;
+    tc.init(lane);
+    unsigned cnt_lo = 0, cnt_hi = 0, tiles_done = 0;
+
+    const long long ntiles = (A.nvox + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * (kThreads / 32);
+    for (long long tile = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+        const long long v = (tile << 5) + lane;
+        const bool act = v < A.nvox;
+        float key[NB];
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            key[i] = CUDART_NAN_F;
+            if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
+        }
+        asm volatile("" ::: "memory");
+        unsigned inv_lo = 0u, inv_hi = 0u;
+        bool flip = false;   // parity of the invalid samples seen so far
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const float d = key[i];
+            const bool ok = (d == d);
+            key[i] = ok ? d : (flip ? -CUDART_INF_F : CUDART_INF_F);
+            if (!ok) {
+                flip = !flip;
+                if (i < 32) inv_lo |= 1u << (i & 31);
+                else inv_hi |= 1u << (i & 31);
+            }
+        }
+        const int n = NB - __popc(inv_lo) - __popc(inv_hi);
+        int ce = 0;
+#define MB_CE(i, j) key_ce_fma(key[i], key[j], one, minus_one); ce++;
+        if constexpr (NB == 4) { MB_SORTNET_4(MB_CE) }
+        else if constexpr (NB == 8) { MB_SORTNET_8(MB_CE) }
+        else if constexpr (NB == 12) { MB_SORTNET_12(MB_CE) }
+        else if constexpr (NB == 16) { MB_SORTNET_16(MB_CE) }
+        else if constexpr (NB == 24) { MB_SORTNET_24(MB_CE) }
+        else if constexpr (NB == 32) { MB_SORTNET_32(MB_CE) }
+        else if constexpr (NB == 48) { MB_SORTNET_48(MB_CE) }
+        else if constexpr (NB == 64) { MB_SORTNET_64(MB_CE) }
+#undef MB_CE
+        // first invalid sample went to +inf: with an odd number of them there is one more +inf than
+        // -inf, so the valid samples occupy slots [a, a+n) with a = floor((NB-n)/2) and the middle
+        // of the valid run is at slot NB/2-1 (odd n) or slots NB/2-1, NB/2 (even n)
+        const double lo = (double)key[NB / 2 - 1];
+        const double hi = (double)key[NB / 2];
+        cnt_lo += __popc(tc.apply(inv_lo));
+        if (NB > 32) cnt_hi += __popc(tc.apply(inv_hi));
+        tiles_done++;
+        if (act) {
+            double med = (n & 1) ? lo : (lo + hi) * 0.5;
+            if (n == 0) med = CUDART_NAN;
+            A.out[v] = med;
+            A.expmap[v] = n;
+        }
+    }
+    const unsigned seen = tiles_done * 32u;
+    if (lane < nfiles) atomicAdd(A.valid_cnt + lane, (unsigned long long)(seen - cnt_lo));
+    if (NB > 32 && 32 + lane < nfiles) atomicAdd(A.valid_cnt + 32 + lane, (unsigned long long)(seen - cnt_hi));
+}
+
+}  // namespace mb
