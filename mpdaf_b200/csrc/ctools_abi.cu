@@ -222,8 +222,8 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
         return MPDAF_B200_OK;
     };
     const long long ntiles = (j.a.nvox + 31) / 32;
-    if (unit) return launch(sigclip_warp_kernel<NB, true, 2>, 0, ntiles);
-    return launch(sigclip_warp_kernel<NB, false, 2>, 0, ntiles);
+    if (unit) return launch(sigclip_warp_kernel<NB, true, 0>, 0, ntiles);
+    return launch(sigclip_warp_kernel<NB, false, 0>, 0, ntiles);
 }
 
 template <int NB>
@@ -240,15 +240,25 @@ int launch_median_warp(const Job& j, int device, cudaStream_t stream)
     char name[64];
     std::snprintf(name, sizeof name, "median_warp<%d>", NB);
     g_last_kernel = name;
-    int per_sm = 0;
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, median_warp_kernel<NB>, kThreads, 0));
-    if (per_sm < 1) per_sm = 1;
-    const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
-    const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-    median_warp_kernel<NB><<<grid, kThreads, 0, stream>>>(s, j.a);
-    MB_CUDA(cudaGetLastError());
-    g_last_launches++;
-    return MPDAF_B200_OK;
+    static const int sort_reps = std::getenv("MPDAF_B200_SORT_REPS") ? std::atoi(std::getenv("MPDAF_B200_SORT_REPS")) : 1;
+    static const int fma_every = std::getenv("MPDAF_B200_FMA_EVERY") ? std::atoi(std::getenv("MPDAF_B200_FMA_EVERY")) : 1;
+    auto launch = [&](auto kernel) -> int {
+        int per_sm = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
+        const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
+        kernel<<<grid, kThreads, 0, stream>>>(s, j.a, sort_reps);
+        MB_CUDA(cudaGetLastError());
+        g_last_launches++;
+        return MPDAF_B200_OK;
+    };
+    if constexpr (NB == 12 || NB == 48) {
+        if (fma_every == 0) return launch(median_warp_kernel<NB, 0>);
+        if (fma_every == 2) return launch(median_warp_kernel<NB, 2>);
+        if (fma_every == 3) return launch(median_warp_kernel<NB, 3>);
+    }
+    return launch(median_warp_kernel<NB, 1>);
 }
 
 template <int MAXN, typename ElemT>

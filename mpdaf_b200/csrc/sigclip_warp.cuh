@@ -32,11 +32,14 @@
 #include "combine_kernels.cuh"
 #include "sigclip_tile.cuh"
 
+#ifndef MB_WARP_BLOCKS
+#define MB_WARP_BLOCKS 4   // resident 128-thread blocks per SM the warp kernel is compiled for
+#endif
+
 namespace mb {
 
 template <int NB>
 struct WarpSmem {
-    float d[NB][32];   // staged samples of the current tile (lookup of rejected samples, fallback)
     float k[NB][32];   // sorted keys, one column per lane
 };
 
@@ -46,6 +49,7 @@ struct BlockSmem {
     double scale[NB];
     double offset[NB];
     double rcp[NB + 1];   // 1.0 / m
+    const float* data[NB];   // exposure base pointers (lane-dependent lookups of rejected samples)
 };
 
 // compare-exchange variants: the max as a + b - min on the ALU (IADD3) or on the FMA pipe (2 IMAD)
@@ -87,13 +91,14 @@ __device__ __forceinline__ void sort_keys_mixed(float (&a)[NB], unsigned one, un
 
 // The reference algorithm restated literally for one voxel (rare fallback path).
 template <int NB, bool UNIT>
-__device__ __noinline__ VoxelResult exact_voxel_w(const float (*d)[32], const double* scale, const double* offset,
-                                                  int lane, int nfiles, int nmax, double lo, double up, int nstop)
+__device__ __noinline__ VoxelResult exact_voxel_w(const float* const* data, long long v, const double* scale,
+                                                  const double* offset, int nfiles, int nmax, double lo, double up,
+                                                  int nstop)
 {
     GenericScratch<NB> g;
     int n = 0;
     for (int i = 0; i < nfiles; i++) {
-        const float x = d[i][lane];
+        const float x = __ldg(data[i] + v);   // the tile's lines are still in L1 / L2
         if (x == x) {
             g.w[n] = UNIT ? (double)x : (offset[i] + (double)x) * scale[i];
             g.file[n] = (unsigned short)i;
@@ -162,7 +167,7 @@ struct TransposeConsts {
 };
 
 template <int NB, bool UNIT, int FMA_EVERY>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, MB_WARP_BLOCKS)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
                     const int phase_lock, unsigned long long* slow_total)
 {
@@ -182,9 +187,9 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         sm.offset[tid] = S.offset[tid];
     }
     if (tid <= NB) sm.rcp[tid] = tid > 0 ? 1.0 / (double)tid : 0.0;
+    if (tid < NB) sm.data[tid] = S.data[tid];
     __syncthreads();   // the only block-wide barrier of the kernel
 
-    float (*sd)[32] = sm.w[wib].d;
     float (*sk)[32] = sm.w[wib].k;
     TransposeConsts tc;
     tc.init(lane);
@@ -241,7 +246,6 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 #pragma unroll
         for (int i = 0; i < NB; i++) {
             const float d = key[i];
-            sd[i][lane] = d;
             const bool ok = (d == d);
             double w;
             if constexpr (UNIT) w = (double)d;
@@ -338,7 +342,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 for (int q = a; q < b; q++) {
                     if (q == na) { q = nb2; if (q >= b) break; }
                     const int i = (int)(__float_as_uint(sk[q][lane]) & 63u);
-                    const double dd = (double)sd[i][lane];
+                    const double dd = (double)__ldg(sm.data[i] + v);   // L1 / L2 hit: loaded by this warp just now
                     const double w = UNIT ? dd : (sm.offset[i] + dd) * sm.scale[i];
                     const double t = w - p;
                     T1 -= t;
@@ -352,7 +356,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         }
         int kept = b - a;
         if (slow) {
-            const VoxelResult r = exact_voxel_w<NB, UNIT>(sd, sm.scale, sm.offset, lane, nfiles, A.nmax, A.nclip_low,
+            const VoxelResult r = exact_voxel_w<NB, UNIT>(sm.data, v, sm.scale, sm.offset, nfiles, A.nmax, A.nclip_low,
                                                           A.nclip_up, nstop);
             mean = r.mean;
             sigma = r.sigma;
@@ -437,10 +441,11 @@ namespace mb {
 // n valid samples is then always at the two fixed middle slots NB/2-1 and NB/2 (odd n: slot
 // NB/2-1 alone), and no data-dependent selection is needed.  The network's compare-exchange is
 // FMNMX + integer a+b-min with the integer part on the FMA pipe (the ALU pipe is the bottleneck
-// of this kernel); per-exposure valid counts come from one 32x32 bit transpose per 32 exposures.
+// of this kernel -- measured: FMNMX 64 lanes/clk/SM, IADD3 more than that, IMAD 64, so the plain
+// FMNMX + IADD3 form sustains ~60 compare-exchanges/clk/SM, twice the 2xIMAD form); per-exposure valid counts come from one 32x32 bit transpose per 32 exposures.
 // ---------------------------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A)
+template <int NB, int FMA_EVERY>
+__global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const int sort_reps)
 {
     const int lane = threadIdx.x & 31;
     const int nfiles = A.nfiles;
@@ -476,17 +481,9 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
             }
         }
         const int n = NB - __popc(inv_lo) - __popc(inv_hi);
-        int ce = 0;
-#define MB_CE(i, j) key_ce_fma(key[i], key[j], one, minus_one); ce++;
-        if constexpr (NB == 4) { MB_SORTNET_4(MB_CE) }
-        else if constexpr (NB == 8) { MB_SORTNET_8(MB_CE) }
-        else if constexpr (NB == 12) { MB_SORTNET_12(MB_CE) }
-        else if constexpr (NB == 16) { MB_SORTNET_16(MB_CE) }
-        else if constexpr (NB == 24) { MB_SORTNET_24(MB_CE) }
-        else if constexpr (NB == 32) { MB_SORTNET_32(MB_CE) }
-        else if constexpr (NB == 48) { MB_SORTNET_48(MB_CE) }
-        else if constexpr (NB == 64) { MB_SORTNET_64(MB_CE) }
-#undef MB_CE
+#pragma unroll 1
+        for (int rep = 0; rep < sort_reps; rep++)   // sort_reps > 1: instruction-cache experiment only
+            sort_keys_mixed<NB, FMA_EVERY>(key, one, minus_one);
         // first invalid sample went to +inf: with an odd number of them there is one more +inf than
         // -inf, so the valid samples occupy slots [a, a+n) with a = floor((NB-n)/2) and the middle
         // of the valid run is at slot NB/2-1 (odd n) or slots NB/2-1, NB/2 (even n)

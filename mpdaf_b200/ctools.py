@@ -24,7 +24,8 @@ HOST, DEVICE = 0, 1
 OK, ERR_ARG, ERR_CUDA, ERR_IO, ERR_SHAPE = 0, 1, 2, 3, 4
 
 try:
-    ctools = load_library("_ctools", LIBRARY_PATH)
+    # MPDAF_B200_LIBNAME selects an alternative build of the library (tuning experiments)
+    ctools = load_library(os.environ.get("MPDAF_B200_LIBNAME", "_ctools"), LIBRARY_PATH)
 except OSError:  # pragma: no cover
     logging.getLogger(__name__).error(
         "mpdaf_b200's CUDA extension `_ctools` is missing; build it with "

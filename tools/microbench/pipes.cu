@@ -74,6 +74,13 @@ KERNEL(k_cvt_down, double a[CH]; int r[CH],
        a[c] = seedd + c; r[c] = c, asm volatile("{.reg .f32 t; .reg .b32 u; cvt.rn.f32.f64 t, %1; mov.b32 u, t; xor.b32 %0, %0, u;}" : "+r"(r[c]) : "d"(a[c])), acc += r[c])  // F2F.F32.F64 + LOP
 KERNEL(k_lds, int a[CH]; __shared__ int sm[TPB * 4]; sm[threadIdx.x] = seedi; sm[threadIdx.x + TPB] = 0,
        a[c] = threadIdx.x * 4, asm volatile("{.reg .b32 t; ld.shared.b32 t, [%0]; add.s32 %0, %0, t;}" : "+r"(a[c])), acc += a[c])  // LDS + IADD (dependent)
+KERNEL(k_imad, int a[CH]; int b = seedi; int d = seedi * 5,
+       a[c] = seedi + c + threadIdx.x, asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[c]) : "r"(b), "r"(d)), acc += a[c])  // IMAD
+KERNEL(k_iadd3, int a[CH]; int b = seedi + threadIdx.x; int d = seedi * 5,
+       a[c] = seedi + c + threadIdx.x, asm volatile("{.reg .b32 t; add.s32 t, %0, %1; sub.s32 %0, t, %2; xor.b32 %0, %0, %1;}" : "+r"(a[c]) : "r"(b), "r"(d)), acc += a[c])  // IADD3 + LOP3
+KERNEL(k_fce_mixed, float a[CH]; float b[CH]; int one = seedi / 3; int mone = -one,
+       a[c] = seedf + c; b[c] = seedf * c,
+       asm volatile("{.reg .f32 t; .reg .b32 x, y, z; min.f32 t, %0, %1; mov.b32 x, %0; mov.b32 y, %1; mov.b32 z, t; mad.lo.s32 x, x, %2, y; mad.lo.s32 x, z, %3, x; mov.b32 %1, x; mov.f32 %0, t;}" : "+f"(a[c]), "+f"(b[c]) : "r"(one), "r"(mone)), acc += (a[c] + b[c]))  // CE = FMNMX + 2 IMAD
 KERNEL(k_f2f_up, float a[CH]; double d[CH],
        a[c] = seedf + c; d[c] = 0, asm volatile("{.reg .f64 t; cvt.f64.f32 t, %1; add.rn.f64 %0, %0, t;}" : "+d"(d[c]) : "f"(a[c])), acc += (float)d[c])  // 1 F2F + 1 DADD
 KERNEL(k_f2f_down, double a[CH]; float f[CH],
@@ -147,6 +154,9 @@ int main()
     run("dsetp+sel", k_dsetp_sel, 2);
     run("f64 cmpxchg", k_dce, 1);
     run("f32 cmpxchg", k_fce, 1);
+    run("imad", k_imad, 1);
+    run("iadd3+lop3", k_iadd3, 2);
+    run("f32 cmpxchg 2xIMAD", k_fce_mixed, 1);
     run("f32 cmpxchg addsub", k_fce_addsub, 1);
     run("shfl+lop", k_shfl, 2);
     run("popc+iadd", k_popc, 2);
