@@ -139,6 +139,62 @@ __device__ __forceinline__ int count_col(const float (*col)[32], int lane, float
     return base + ((LE ? (kv <= x) : (kv < x)) ? 1 : 0);
 }
 
+// Rare path: a key lies within the key-space uncertainty of a clip bound.  Recover the exact
+// median from the exposure indices carried by the median keys (only possible when their
+// truncated-key buckets hold a single sample), recompute the bounds, and classify the few band
+// keys from their exact float64 values.  Returns false when even that cannot decide (then the
+// voxel goes to exact_voxel_w).  On success lo_in / up_in are the exact counts of keys at or
+// below the low bound / strictly below the high bound (positions in the whole column).
+template <int NB, bool UNIT>
+__device__ __noinline__ bool refine_band(const float (*sk)[32], int lane, const float* const* data, long long v,
+                                         const double* scale, const double* offset, int ih, int il, int m,
+                                         double sigma, double nlo, double nup, double clo, double cup, double T,
+                                         int& lo_in, int& up_in)
+{
+    auto bucket = [](float k) { return __float_as_uint(k) & ~63u; };
+    auto exact_w = [&](float k) {
+        const int i = (int)(__float_as_uint(k) & 63u);
+        const double dd = (double)__ldg(data[i] + v);
+        return UNIT ? dd : (offset[i] + dd) * scale[i];
+    };
+    const float kh = sk[ih][lane], kl = sk[il][lane];
+    if (ih + 1 < NB && bucket(sk[ih + 1][lane]) == bucket(kh)) return false;
+    if (il > 0 && bucket(sk[il - 1][lane]) == bucket(kl)) return false;
+    if (il != ih && bucket(kl) == bucket(kh)) return false;
+    const double wh = exact_w(kh), wl = exact_w(kl);
+    const double med = (m & 1) ? wh : (wh + wl) * 0.5;          // tools.c:45-48
+    const double clo_x = med - (nlo * sigma);
+    const double cup_x = med + (nup * sigma);
+    // what is left is the sigma uncertainty (2^-28 relative) and the final roundings
+    const double T2 = 0x1p-26 * (nlo + nup) * sigma + 0x1p-44 * (fabs(clo_x) + fabs(cup_x)) + 0x1p-300;
+    const int lo_out = count_col<NB, true>(sk, lane, __double2float_rd(clo - T));
+    const int lo_in0 = count_col<NB, true>(sk, lane, __double2float_ru(clo + T));
+    const int up_in0 = count_col<NB, false>(sk, lane, __double2float_rd(cup - T));
+    const int up_out = count_col<NB, false>(sk, lane, __double2float_ru(cup + T));
+    if (lo_in0 > up_in0) return false;                           // bands overlap: degenerate window
+    int first_inside = lo_in0;
+    bool seen = false;
+    for (int q = lo_out; q < lo_in0; q++) {                      // low band: outside ... then inside ...
+        const double w = exact_w(sk[q][lane]);
+        if (fabs(w - clo_x) <= T2) return false;
+        const bool inside = w > clo_x;
+        if (inside && !seen) { first_inside = q; seen = true; }
+        if (!inside && seen) return false;
+    }
+    int first_outside = up_out;
+    seen = false;
+    for (int q = up_in0; q < up_out; q++) {                      // high band: inside ... then outside ...
+        const double w = exact_w(sk[q][lane]);
+        if (fabs(w - cup_x) <= T2) return false;
+        const bool inside = w < cup_x;
+        if (!inside && !seen) { first_outside = q; seen = true; }
+        if (inside && seen) return false;
+    }
+    lo_in = first_inside;
+    up_in = first_outside;
+    return true;
+}
+
 // 32x32 bit-matrix transpose across the warp: on return bit l of lane i = bit i of lane l's x.
 struct TransposeConsts {
     unsigned sel[5];   // per-stage bit-select mask for this lane
@@ -327,11 +383,13 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 // band checks: no key in (clo - T, clo + T] and none in [cup - T, cup + T)
                 const bool lo_band = lo_in > 0 && !(sk[lo_in - 1][lane] <= f_lo_out);
                 const bool up_band = up_in < NB && (sk[up_in < NB ? up_in : NB - 1][lane] < f_up_out);
+                if (lo_band || up_band) {
+                    // ~1e-4 of the voxels: settle the band keys from their exact values
+                    if (!refine_band<NB, UNIT>(sk, lane, sm.data, v, sm.scale, sm.offset, ih, il, m, sigma, A.nclip_low,
+                                               A.nclip_up, clo, cup, T, lo_in, up_in)) { slow = true; break; }
+                }
                 lo_in = min(max(lo_in, a), b);
                 up_in = min(max(up_in, a), b);
-                // a band hit outside the current window is harmless only if it is not adjacent to it;
-                // keep it simple and conservative: any band hit defers to the exact path
-                if (lo_band || up_band) { slow = true; break; }
                 const int na = lo_in;                                     // first kept position
                 const int nb2 = max(up_in, na);                           // one past the last kept
                 const int ni = nb2 - na;
