@@ -68,7 +68,8 @@ def main():
     bpv = n * 4 * a + (12 if args.median else 20)
     res = dict(kernel=ctools.mpdaf_b200_last_kernel_name().decode(), n=n, nz=nz, ms=ms,
                gvox_exp_s=n * nvox / ms / 1e6, gbs=bpv * nvox / ms / 1e6, bytes_per_voxel=bpv,
-               rejected=int(valid.sum() - select.sum()) if not args.median else None)
+               rejected=int(valid.sum() - select.sum()) if not args.median else None,
+               slow_voxels=int(ctools.mpdaf_b200_slow_voxels(0, 1)))
     if args.check:
         import oracle
         cz = min(nz, 2)
