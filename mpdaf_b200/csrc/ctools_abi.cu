@@ -103,7 +103,7 @@ struct Job {
 
 int bucket_of(int nfiles)
 {
-    const int sizes[] = {4, 8, 12, 16, 24, 32, 48, 64};
+    const int sizes[] = {4, 8, 12, 16, 24, 32, 48, 64, 96, 128};
     for (int s : sizes)
         if (nfiles <= s) return s;
     return 0;
@@ -215,8 +215,8 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
         if (per_sm < 1) per_sm = 1;
         const long long nblocks = (t1 - t0 + (kThreads / 32) - 1) / (kThreads / 32);
         const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-        static const int phase_lock = std::getenv("MPDAF_B200_PHASE_LOCK") ? std::atoi(std::getenv("MPDAF_B200_PHASE_LOCK")) : 0;
-        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, t0, t1, phase_lock, g_dev[device].slow);
+        static const int flags = std::getenv("MPDAF_B200_WARP_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : 0;
+        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, t0, t1, flags, g_dev[device].slow);
         MB_CUDA(cudaGetLastError());
         g_last_launches++;
         return MPDAF_B200_OK;
@@ -309,6 +309,8 @@ int enqueue_combine(const Job& j, int device, cudaStream_t stream)
             case 32: return launch_warp<32>(j, unit, device, stream);
             case 48: return launch_warp<48>(j, unit, device, stream);
             case 64: return launch_warp<64>(j, unit, device, stream);
+            case 96: return launch_warp<96>(j, unit, device, stream);
+            case 128: return launch_warp<128>(j, unit, device, stream);
         }
     }
     if (reg_ok && j.median && which == "warp") {
@@ -321,6 +323,8 @@ int enqueue_combine(const Job& j, int device, cudaStream_t stream)
             case 32: return launch_median_warp<32>(j, device, stream);
             case 48: return launch_median_warp<48>(j, device, stream);
             case 64: return launch_median_warp<64>(j, device, stream);
+            case 96: return launch_median_warp<96>(j, device, stream);
+            case 128: return launch_median_warp<128>(j, device, stream);
         }
     }
     if (reg_ok && !j.median && !use_v1) {

@@ -38,6 +38,52 @@
 
 namespace mb {
 
+// Key layout: float32(w) with the low kIdxBits mantissa bits replaced by the exposure index.
+template <int NB> struct KeyBits { static constexpr int idx_bits = NB <= 64 ? 6 : 7; };
+template <int NB> __device__ __forceinline__ constexpr unsigned idx_mask() { return (1u << KeyBits<NB>::idx_bits) - 1u; }
+
+// Per-voxel exposure set (bit i = exposure i), 32-bit words so that constant-index updates stay
+// single LOP3s for any depth up to 128.
+template <int NB>
+struct ExpSet {
+    static constexpr int W = (NB + 31) / 32;
+    unsigned w[W];
+    __device__ __forceinline__ ExpSet()
+    {
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] = 0u;
+    }
+    __device__ __forceinline__ void set(int i) { w[i >> 5] |= 1u << (i & 31); }              // i constant after unrolling
+    __device__ __forceinline__ bool test(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+    __device__ __forceinline__ void set_dyn(int i)
+    {
+#pragma unroll
+        for (int k = 0; k < W; k++) w[k] |= ((i >> 5) == k) ? (1u << (i & 31)) : 0u;
+    }
+    __device__ __forceinline__ int count() const
+    {
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < W; k++) c += __popc(w[k]);
+        return c;
+    }
+    __device__ __forceinline__ ExpSet operator|(const ExpSet& o) const
+    {
+        ExpSet r;
+#pragma unroll
+        for (int k = 0; k < W; k++) r.w[k] = w[k] | o.w[k];
+        return r;
+    }
+};
+
+template <int NB>
+struct VoxelResultN {
+    double mean;
+    double sigma;
+    int kept;
+    ExpSet<NB> rejected;   // exposure valid but clipped
+};
+
 template <int NB>
 struct WarpSmem {
     float k[NB][32];   // sorted keys, one column per lane
@@ -86,14 +132,16 @@ __device__ __forceinline__ void sort_keys_mixed(float (&a)[NB], unsigned one, un
     else if constexpr (NB == 32) { MB_SORTNET_32(MB_CE) }
     else if constexpr (NB == 48) { MB_SORTNET_48(MB_CE) }
     else if constexpr (NB == 64) { MB_SORTNET_64(MB_CE) }
+    else if constexpr (NB == 96) { MB_SORTNET_96(MB_CE) }
+    else if constexpr (NB == 128) { MB_SORTNET_128(MB_CE) }
 #undef MB_CE
 }
 
 // The reference algorithm restated literally for one voxel (rare fallback path).
 template <int NB, bool UNIT>
-__device__ __noinline__ VoxelResult exact_voxel_w(const float* const* data, long long v, const double* scale,
-                                                  const double* offset, int nfiles, int nmax, double lo, double up,
-                                                  int nstop)
+__device__ __noinline__ VoxelResultN<NB> exact_voxel_w(const float* const* data, long long v, const double* scale,
+                                                       const double* offset, int nfiles, int nmax, double lo, double up,
+                                                       int nstop)
 {
     GenericScratch<NB> g;
     int n = 0;
@@ -106,18 +154,18 @@ __device__ __noinline__ VoxelResult exact_voxel_w(const float* const* data, long
             n++;
         }
     }
-    VoxelResult r;
+    VoxelResultN<NB> r;
     r.mean = CUDART_NAN;
     r.sigma = 0.0;
     r.kept = n;
-    r.rejected = 0ull;
     if (n == 1) r.mean = g.w[0];
     if (n >= 2) {
         r.kept = clip_generic<NB>(g, n, nmax, lo, up, nstop, 0, r.mean, r.sigma);
-        unsigned long long keep = 0ull, valid = 0ull;
-        for (int k = 0; k < r.kept; k++) keep |= 1ull << g.file[g.idx[k]];
-        for (int k = 0; k < n; k++) valid |= 1ull << g.file[k];
-        r.rejected = valid & ~keep;
+        ExpSet<NB> keep, valid;
+        for (int k = 0; k < r.kept; k++) keep.set_dyn(g.file[g.idx[k]]);
+        for (int k = 0; k < n; k++) valid.set_dyn(g.file[k]);
+#pragma unroll
+        for (int k = 0; k < ExpSet<NB>::W; k++) r.rejected.w[k] = valid.w[k] & ~keep.w[k];
     }
     return r;
 }
@@ -151,9 +199,9 @@ __device__ __noinline__ bool refine_band(const float (*sk)[32], int lane, const 
                                          double sigma, double nlo, double nup, double clo, double cup, double T,
                                          int& lo_in, int& up_in)
 {
-    auto bucket = [](float k) { return __float_as_uint(k) & ~63u; };
+    auto bucket = [](float k) { return __float_as_uint(k) & ~idx_mask<NB>(); };
     auto exact_w = [&](float k) {
-        const int i = (int)(__float_as_uint(k) & 63u);
+        const int i = (int)(__float_as_uint(k) & idx_mask<NB>());
         const double dd = (double)__ldg(data[i] + v);
         return UNIT ? dd : (offset[i] + dd) * scale[i];
     };
@@ -222,13 +270,21 @@ struct TransposeConsts {
     }
 };
 
+// resident 128-thread blocks per SM each depth is compiled for (register budget 65536 / (128 * blocks))
+template <int NB> struct WarpBlocks { static constexpr int value = NB <= 64 ? MB_WARP_BLOCKS : (NB <= 96 ? 3 : 2); };
+
 template <int NB, bool UNIT, int FMA_EVERY>
-__global__ void __launch_bounds__(kThreads, MB_WARP_BLOCKS)
+__global__ void __launch_bounds__(kThreads, WarpBlocks<NB>::value)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
-                    const int phase_lock, unsigned long long* slow_total)
+                    const int flags, unsigned long long* slow_total)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BlockSmem<NB>& sm = *reinterpret_cast<BlockSmem<NB>*>(smem_raw);
+    constexpr int W = ExpSet<NB>::W;
+    constexpr unsigned IDX = (1u << KeyBits<NB>::idx_bits) - 1u;
+    // key-space error model: float32 rounding + truncation of idx_bits mantissa bits is below
+    // 2^-(23 - idx_bits) * 1.01 relative; the margins use four times that
+    constexpr double KEPS = NB <= 64 ? 0x1p-15 : 0x1p-14;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int wib = tid >> 5;
@@ -238,32 +294,36 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     const unsigned one = (unsigned)(A.nfiles > 0);           // opaque 1 / -1 for the IMAD form
     const unsigned minus_one = 0u - one;
 
-    if (tid < NB) {
-        sm.scale[tid] = S.scale[tid];
-        sm.offset[tid] = S.offset[tid];
+    for (int i = tid; i < NB; i += kThreads) {
+        sm.scale[i] = S.scale[i];
+        sm.offset[i] = S.offset[i];
+        sm.data[i] = S.data[i];
     }
-    if (tid <= NB) sm.rcp[tid] = tid > 0 ? 1.0 / (double)tid : 0.0;
-    if (tid < NB) sm.data[tid] = S.data[tid];
-    __syncthreads();   // the only block-wide barrier of the kernel
+    for (int i = tid; i <= NB; i += kThreads) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
+    __syncthreads();   // the only block-wide barrier of the kernel (unless flags & 1)
 
     float (*sk)[32] = sm.w[wib].k;
     TransposeConsts tc;
     tc.init(lane);
 
-    unsigned cnt_inval_lo = 0, cnt_drop_lo = 0, cnt_hi = 0, cnt_hi2 = 0;   // per-lane exposure counters
+    // per-lane exposure counters: lane l counts exposure 32*k + l (invalid / dropped samples)
+    unsigned cnt_inval[W], cnt_drop[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { cnt_inval[k] = 0u; cnt_drop[k] = 0u; }
     unsigned tiles_done = 0, slow_count = 0;
 
     const long long ntiles = tile_end;
     const long long wstride = (long long)gridDim.x * (kThreads / 32);
     long long tile0 = tile_begin + (long long)blockIdx.x * (kThreads / 32);
 
-    // L2 prefetch of a tile's rows: lane l touches rows l and l + 32 (one 128-byte line each)
-    const bool l1 = (phase_lock & 2) == 0;   // prefetch into L1 (measured 12 % faster than L2 only)
+    // prefetch of a tile's rows: lane l touches rows l, l + 32, ... (one 128-byte line each);
+    // into L1 by default (measured 12 % faster than L2 only; flags & 2 selects L2)
+    const bool l1 = (flags & 2) == 0;
     auto prefetch_rows = [&](bool stat, long long t) {
         const long long v0 = t << 5;
         if (v0 + 31 >= A.nvox) return;
 #pragma unroll
-        for (int r = 0; r < (NB + 31) / 32; r++) {
+        for (int r = 0; r < W; r++) {
             const int i = lane + 32 * r;
             if (i < nfiles) {
                 const float* row = stat ? S.var[i] : S.data[i];
@@ -277,9 +337,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     // The trip count is uniform per block so that the optional per-tile barrier is legal; a warp
     // whose last tile lies beyond the range runs it with every lane idle.
     for (; tile0 < ntiles; tile0 += wstride) {
-        // phase lock: the four warps of a block start every tile together, so they walk the
-        // (large, unrolled) instruction stream nearly in step and share instruction-cache lines
-        if (phase_lock) __syncthreads();
+        // flags & 1 (experiment, slower): the four warps of a block start every tile together
+        if (flags & 1) __syncthreads();
         const long long tile = tile0 + wib;
         const long long v = (tile << 5) + lane;
         const bool act = tile < ntiles && v < A.nvox;
@@ -298,7 +357,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         asm volatile("" ::: "memory");
 
         // ---- pass 1: exposure order.  w, exact sum, shifted moments, keys ----------------------
-        unsigned long long inval = 0ull;
+        ExpSet<NB> inval;
         double sum = 0.0, T1 = 0.0, S2 = 0.0, p = 0.0;
         bool have_p = false;
 #pragma unroll
@@ -318,15 +377,15 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 T1 += t;
                 S2 = __fma_rn(t, t, S2);
             } else {
-                inval |= 1ull << i;
+                inval.set(i);
             }
             float kf;
             if constexpr (UNIT) kf = d;
             else kf = __double2float_rn(w);
-            const unsigned kb = (__float_as_uint(kf) & ~63u) | (unsigned)i;
-            key[i] = fminf(__uint_as_float(kb), __uint_as_float(0x7F7FFFC0u | (unsigned)i));  // NaN -> sentinel
+            const unsigned kb = (__float_as_uint(kf) & ~IDX) | (unsigned)i;
+            key[i] = fminf(__uint_as_float(kb), __uint_as_float((0x7F7FFFFFu & ~IDX) | (unsigned)i));  // NaN -> sentinel
         }
-        const int n = NB - __popcll(inval);
+        const int n = NB - inval.count();
 
         sort_keys_mixed<NB, FMA_EVERY>(key, one, minus_one);
 #pragma unroll
@@ -347,7 +406,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         double mean = sum / (double)n;             // n == 0 -> NaN (merging.c:439)
         double sigma = 0.0;
         int a = 0, b = n;
-        unsigned long long rejected = 0ull;
+        ExpSet<NB> rejected;
         bool slow = false;
         if (n >= 2) {
             const double S2_0 = S2;
@@ -366,8 +425,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 sigma = sqrt(var_k);
                 const int ih = a + (m >> 1);
                 const int il = ih - 1 + (m & 1);
-                const float kh = __uint_as_float(__float_as_uint(sk[ih][lane]) & ~63u);
-                const float kl = __uint_as_float(__float_as_uint(sk[il][lane]) & ~63u);
+                const float kh = __uint_as_float(__float_as_uint(sk[ih][lane]) & ~IDX);
+                const float kl = __uint_as_float(__float_as_uint(sk[il][lane]) & ~IDX);
                 const double med = ((double)kh + (double)kl) * 0.5;
                 const double amax = fmax(fabs((double)kh), fabs((double)kl));
                 const double clo = med - (A.nclip_low * sigma);
@@ -375,7 +434,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 // total uncertainty of a key against a bound: median from truncated keys,
                 // sigma from reordered sums, key truncation of the sample itself
                 const double spread = (A.nclip_low + A.nclip_up) * sigma;
-                const double T = 0x1p-15 * amax + 0x1p-26 * spread + 0x1p-15 * (fabs(clo) + fabs(cup)) + 0x1p-120;
+                const double T = KEPS * amax + 0x1p-26 * spread + KEPS * (fabs(clo) + fabs(cup)) + 0x1p-120;
                 if (!(T < 0x1p120)) { slow = true; break; }   // NaN / inf bounds: let the exact path decide
                 // keys certainly at or below the low bound / certainly below the high bound
                 const float f_lo_in = __double2float_ru(clo + T), f_lo_out = __double2float_rd(clo - T);
@@ -398,16 +457,16 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 if (ni < nstop || ni == m) break;                         // tools.c:100-103
                 if (it <= 0) break;                                       // tools.c:104
                 it--;
-                // drop the rejected samples [a,na) and [nb2,b): exact w recomputed from the staged d
+                // drop the rejected samples [a,na) and [nb2,b): exact w recomputed from the samples
                 for (int q = a; q < b; q++) {
                     if (q == na) { q = nb2; if (q >= b) break; }
-                    const int i = (int)(__float_as_uint(sk[q][lane]) & 63u);
+                    const int i = (int)(__float_as_uint(sk[q][lane]) & IDX);
                     const double dd = (double)__ldg(sm.data[i] + v);   // L1 / L2 hit: loaded by this warp just now
                     const double w = UNIT ? dd : (sm.offset[i] + dd) * sm.scale[i];
                     const double t = w - p;
                     T1 -= t;
                     S2 -= t * t;
-                    rejected |= 1ull << i;
+                    rejected.set_dyn(i);
                 }
                 a = na;
                 b = nb2;
@@ -416,8 +475,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         }
         int kept = b - a;
         if (slow) {
-            const VoxelResult r = exact_voxel_w<NB, UNIT>(sm.data, v, sm.scale, sm.offset, nfiles, A.nmax, A.nclip_low,
-                                                          A.nclip_up, nstop);
+            const VoxelResultN<NB> r = exact_voxel_w<NB, UNIT>(sm.data, v, sm.scale, sm.offset, nfiles, A.nmax,
+                                                               A.nclip_low, A.nclip_up, nstop);
             mean = r.mean;
             sigma = r.sigma;
             kept = r.kept;
@@ -427,25 +486,25 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         __syncwarp();
 
         // ---- propagated variance over the kept set --------------------------------------------
-        const unsigned long long dropped = inval | rejected;
+        const ExpSet<NB> dropped = inval | rejected;
         double vsum = 0.0;
         if (want_var) {
 #pragma unroll
             for (int i = 0; i < NB; i++)
-                if (!((dropped >> i) & 1ull)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
+                if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
         }
 
         // ---- per-exposure counters: transpose the lanes' masks, one POPC per lane --------------
-        cnt_inval_lo += __popc(tc.apply((unsigned)inval));
-        cnt_drop_lo += __popc(tc.apply((unsigned)dropped));
-        if (NB > 32) {
-            // exposures 32..63 (NB <= 48: 16 bits each): invalid in the low half, dropped in the high half
-            if constexpr (NB <= 48) {
-                const unsigned packed = ((unsigned)(inval >> 32) & 0xFFFFu) | ((unsigned)(dropped >> 32) << 16);
-                cnt_hi += __popc(tc.apply(packed));
-            } else {
-                cnt_hi += __popc(tc.apply((unsigned)(inval >> 32)));
-                cnt_hi2 += __popc(tc.apply((unsigned)(dropped >> 32)));
+        if constexpr (NB > 32 && NB <= 48) {
+            // exposures 32..47: invalid in the low half-word, dropped in the high half-word
+            cnt_inval[0] += __popc(tc.apply(inval.w[0]));
+            cnt_drop[0] += __popc(tc.apply(dropped.w[0]));
+            cnt_inval[1] += __popc(tc.apply((inval.w[1] & 0xFFFFu) | (dropped.w[1] << 16)));
+        } else {
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                cnt_inval[k] += __popc(tc.apply(inval.w[k]));
+                cnt_drop[k] += __popc(tc.apply(dropped.w[k]));
             }
         }
         tiles_done++;
@@ -468,22 +527,24 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 
     // ---- flush: valid = lanes seen - invalid, selected = lanes seen - dropped -----------------
     const unsigned seen = tiles_done * 32u;
-    if (lane < nfiles) {
-        atomicAdd(A.valid_cnt + lane, (unsigned long long)(seen - cnt_inval_lo));
-        atomicAdd(A.select_cnt + lane, (unsigned long long)(seen - cnt_drop_lo));
-    }
-    if (NB > 32 && NB <= 48) {
+    if constexpr (NB > 32 && NB <= 48) {
+        if (lane < nfiles) {
+            atomicAdd(A.valid_cnt + lane, (unsigned long long)(seen - cnt_inval[0]));
+            atomicAdd(A.select_cnt + lane, (unsigned long long)(seen - cnt_drop[0]));
+        }
         const int e = 32 + (lane & 15);
         if (e < nfiles) {
-            if (lane < 16) atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_hi));
-            else atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_hi));
+            if (lane < 16) atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_inval[1]));
+            else atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_inval[1]));
         }
-    }
-    if (NB > 48) {
-        const int e = 32 + lane;
-        if (e < nfiles) {
-            atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_hi));
-            atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_hi2));
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; k++) {
+            const int e = 32 * k + lane;
+            if (e < nfiles) {
+                atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_inval[k]));
+                atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_drop[k]));
+            }
         }
     }
     if (slow_total != nullptr && slow_count) atomicAdd(slow_total, (unsigned long long)slow_count);
@@ -507,13 +568,17 @@ namespace mb {
 template <int NB, int FMA_EVERY>
 __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const int sort_reps)
 {
+    constexpr int W = ExpSet<NB>::W;
     const int lane = threadIdx.x & 31;
     const int nfiles = A.nfiles;
     const unsigned one = (unsigned)(A.nfiles > 0);
     const unsigned minus_one = 0u - one;
     TransposeConsts tc;
     tc.init(lane);
-    unsigned cnt_lo = 0, cnt_hi = 0, tiles_done = 0;
+    unsigned cnt[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) cnt[k] = 0u;
+    unsigned tiles_done = 0;
 
     const long long ntiles = (A.nvox + 31) >> 5;
     const long long wstride = (long long)gridDim.x * (kThreads / 32);
@@ -527,7 +592,7 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
             if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
         }
         asm volatile("" ::: "memory");
-        unsigned inv_lo = 0u, inv_hi = 0u;
+        ExpSet<NB> inval;
         bool flip = false;   // parity of the invalid samples seen so far
 #pragma unroll
         for (int i = 0; i < NB; i++) {
@@ -536,11 +601,10 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
             key[i] = ok ? d : (flip ? -CUDART_INF_F : CUDART_INF_F);
             if (!ok) {
                 flip = !flip;
-                if (i < 32) inv_lo |= 1u << (i & 31);
-                else inv_hi |= 1u << (i & 31);
+                inval.set(i);
             }
         }
-        const int n = NB - __popc(inv_lo) - __popc(inv_hi);
+        const int n = NB - inval.count();
 #pragma unroll 1
         for (int rep = 0; rep < sort_reps; rep++)   // sort_reps > 1: instruction-cache experiment only
             sort_keys_mixed<NB, FMA_EVERY>(key, one, minus_one);
@@ -549,8 +613,8 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
         // of the valid run is at slot NB/2-1 (odd n) or slots NB/2-1, NB/2 (even n)
         const double lo = (double)key[NB / 2 - 1];
         const double hi = (double)key[NB / 2];
-        cnt_lo += __popc(tc.apply(inv_lo));
-        if (NB > 32) cnt_hi += __popc(tc.apply(inv_hi));
+#pragma unroll
+        for (int k = 0; k < W; k++) cnt[k] += __popc(tc.apply(inval.w[k]));
         tiles_done++;
         if (act) {
             double med = (n & 1) ? lo : (lo + hi) * 0.5;
@@ -560,8 +624,11 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
         }
     }
     const unsigned seen = tiles_done * 32u;
-    if (lane < nfiles) atomicAdd(A.valid_cnt + lane, (unsigned long long)(seen - cnt_lo));
-    if (NB > 32 && 32 + lane < nfiles) atomicAdd(A.valid_cnt + 32 + lane, (unsigned long long)(seen - cnt_hi));
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        const int e = 32 * k + lane;
+        if (e < nfiles) atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt[k]));
+    }
 }
 
 }  // namespace mb

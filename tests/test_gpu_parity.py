@@ -21,7 +21,7 @@ def cuda():
 
 
 @pytest.mark.parametrize("location", ["device", "host"])
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 12, 13, 16, 24, 25, 32, 33, 48, 49, 64])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 12, 13, 16, 24, 25, 32, 33, 48, 49, 64, 65, 96, 97, 128])
 def test_register_kernels_every_bucket(n, location):
     rng = np.random.default_rng(100 + n)
     shape = (6, 11, 13)          # 858 voxels: not a multiple of the block size
@@ -86,9 +86,9 @@ def test_clip_parameters(nmax, lo, up, nstop, ties):
     assert_same_result(got, want)
 
 
-@pytest.mark.parametrize("n", [5, 48, 70, 130])
+@pytest.mark.parametrize("n", [5, 48, 70, 96, 128, 130, 200])
 @pytest.mark.parametrize("vartype", ["propagate", "stat_mean"])
-def test_mad_and_deep_stacks_use_the_generic_kernels(n, vartype):
+def test_mad_and_deep_stacks(n, vartype):
     rng = np.random.default_rng(n)
     data, var = random_stack(rng, n, (3, 5, 7), nan_frac=0.1, outlier_frac=0.05)
     kw = dict(scales=np.linspace(0.9, 1.1, n), offsets=np.linspace(-0.1, 0.1, n), nclip=3.0, vartype=vartype)
@@ -96,8 +96,10 @@ def test_mad_and_deep_stacks_use_the_generic_kernels(n, vartype):
         want = oracle.combine_port(data, var, mad=mad, **kw)
         got = cuda().combine_cuda(data, var, mad=mad, **kw)
         assert_same_result(got, want)
-        if mad or n > 64:
+        if mad or n > 128:
             assert "generic" in cuda().kernel_name()
+        else:
+            assert "warp" in cuda().kernel_name()
     if n > 64:
         assert_same_result(cuda().median_cuda(data), oracle.median_port(data), median=True)
 
@@ -255,7 +257,7 @@ def test_random_fuzz_against_oracle():
     rng = np.random.default_rng(2025)
     c = cuda()
     for trial in range(40):
-        n = int(rng.integers(2, 65))
+        n = int(rng.integers(2, 129))
         shape = (2, int(rng.integers(3, 9)), int(rng.integers(3, 40)))
         data, var = random_stack(rng, n, shape, nan_frac=float(rng.uniform(0, 0.4)),
                                  outlier_frac=float(rng.uniform(0, 0.15)), ties=bool(trial % 5 == 0))
