@@ -211,12 +211,12 @@ int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
         const int smem = (int)sizeof(BlockSmem<NB>);
         MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWT, smem));
         if (per_sm < 1) per_sm = 1;
-        const long long nblocks = (t1 - t0 + (kThreads / 32) - 1) / (kThreads / 32);
+        const long long nblocks = (t1 - t0 + (kWT / 32) - 1) / (kWT / 32);
         const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-        static const int flags = std::getenv("MPDAF_B200_WARP_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : 0;
-        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, t0, t1, flags, g_dev[device].slow);
+        static const int flags = std::getenv("MPDAF_B200_WARP_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : (NB >= 24 ? 1 : 0);
+        kernel<<<grid, kWT, smem, stream>>>(s, j.a, t0, t1, flags, g_dev[device].slow);
         MB_CUDA(cudaGetLastError());
         g_last_launches++;
         return MPDAF_B200_OK;

@@ -32,6 +32,9 @@
 #include "combine_kernels.cuh"
 #include "sigclip_tile.cuh"
 
+#ifndef MB_WARP_THREADS
+#define MB_WARP_THREADS 128   // threads per block of the warp-tiled sigma-clip kernel
+#endif
 #ifndef MB_WARP_BLOCKS
 #define MB_WARP_BLOCKS 4   // resident 128-thread blocks per SM the warp kernel is compiled for
 #endif
@@ -89,9 +92,11 @@ struct WarpSmem {
     float k[NB][32];   // sorted keys, one column per lane
 };
 
+constexpr int kWT = MB_WARP_THREADS;
+
 template <int NB>
 struct BlockSmem {
-    WarpSmem<NB> w[kThreads / 32];
+    WarpSmem<NB> w[kWT / 32];
     double scale[NB];
     double offset[NB];
     double rcp[NB + 1];   // 1.0 / m
@@ -271,10 +276,10 @@ struct TransposeConsts {
 };
 
 // resident 128-thread blocks per SM each depth is compiled for (register budget 65536 / (128 * blocks))
-template <int NB> struct WarpBlocks { static constexpr int value = NB <= 64 ? MB_WARP_BLOCKS : (NB <= 96 ? 3 : 2); };
+template <int NB> struct WarpBlocks { static constexpr int value = (NB <= 64 ? MB_WARP_BLOCKS : (NB <= 96 ? 3 : 2)) * 128 / kWT; };
 
 template <int NB, bool UNIT, int FMA_EVERY>
-__global__ void __launch_bounds__(kThreads, WarpBlocks<NB>::value)
+__global__ void __launch_bounds__(kWT, WarpBlocks<NB>::value)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
                     const int flags, unsigned long long* slow_total)
 {
@@ -294,12 +299,12 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     const unsigned one = (unsigned)(A.nfiles > 0);           // opaque 1 / -1 for the IMAD form
     const unsigned minus_one = 0u - one;
 
-    for (int i = tid; i < NB; i += kThreads) {
+    for (int i = tid; i < NB; i += kWT) {
         sm.scale[i] = S.scale[i];
         sm.offset[i] = S.offset[i];
         sm.data[i] = S.data[i];
     }
-    for (int i = tid; i <= NB; i += kThreads) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
+    for (int i = tid; i <= NB; i += kWT) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
     __syncthreads();   // the only block-wide barrier of the kernel (unless flags & 1)
 
     float (*sk)[32] = sm.w[wib].k;
@@ -313,8 +318,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     unsigned tiles_done = 0, slow_count = 0;
 
     const long long ntiles = tile_end;
-    const long long wstride = (long long)gridDim.x * (kThreads / 32);
-    long long tile0 = tile_begin + (long long)blockIdx.x * (kThreads / 32);
+    const long long wstride = (long long)gridDim.x * (kWT / 32);
+    long long tile0 = tile_begin + (long long)blockIdx.x * (kWT / 32);
 
     // prefetch of a tile's rows: lane l touches rows l, l + 32, ... (one 128-byte line each);
     // into L1 by default (measured 12 % faster than L2 only; flags & 2 selects L2)
