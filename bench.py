@@ -123,7 +123,36 @@ def cpu_sample_setup(nz, tmpdir):
     return files
 
 
-def cpu_reference_run(nz, steps, warmup, keep=False):
+def dropin_files_run(files, nz, scales, offsets, ref_result):
+    """The drop-in symbol itself (`mpdaf_merging_sigma_clipping`, FITS file names in, NumPy buffers
+    out -- exactly the call lib/mpdaf/obj/cubelist.py:512-515 makes) on the same FITS files the
+    reference just combined: wall-clock time including FITS reading, H2D, kernel and D2H."""
+    import ctypes
+    from mpdaf_b200.ctools import ctools
+    nvox = nz * PLANE
+    out, outvar = np.empty(nvox), np.empty(nvox)
+    expmap = np.empty(nvox, dtype=np.intc)
+    names = "\n".join(files).encode("utf8")
+    best = None
+    for _ in range(3):
+        sel, val = np.zeros(NFILES, dtype=np.intc), np.zeros(NFILES, dtype=np.intc)
+        t0 = time.perf_counter()
+        rc = ctools.mpdaf_merging_sigma_clipping(ctypes.c_char_p(names), out, outvar, expmap, scales, offsets, sel, val,
+                                                 CLIP["nmax"], CLIP["nclip"], CLIP["nclip"], CLIP["nstop"], 0, 0)
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            return {"error": f"rc={rc}"}
+        best = dt if best is None else min(best, dt)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = float(np.nanmax(np.abs(out - ref_result["data"]) / np.abs(ref_result["data"])))
+    ok = bool(np.array_equal(expmap, ref_result["expmap"]) and np.array_equal(sel, ref_result["select_pix"])
+              and np.array_equal(val, ref_result["valid_pix"]) and rel <= 1e-6)
+    return {"seconds": best, "value": NFILES * nvox / best / 1e9, "unit": "Gvoxel*exposures/s",
+            "parity_with_reference_ok": ok, "max_rel_err_data": rel,
+            "what": "mpdaf_merging_sigma_clipping(file names) on the reference's own FITS inputs, FITS decode included"}
+
+
+def cpu_reference_run(nz, steps, warmup, keep=False, dropin=False):
     """Times mpdaf_merging_sigma_clipping of the compiled reference on nz planes of the workload."""
     import oracle
     from mpdaf_b200 import synth
@@ -157,13 +186,16 @@ def cpu_reference_run(nz, steps, warmup, keep=False):
             t0 = time.perf_counter()
             result = run()
             times.append(time.perf_counter() - t0)
+        extra = None
+        if dropin and kind == "reference":
+            extra = dropin_files_run(files, nz, scales, offsets, result)
     finally:
         if not keep:
             shutil.rmtree(tmpdir, ignore_errors=True)
     sec = float(np.mean(times))
     value = NFILES * nz * PLANE / sec / 1e9
     return dict(value=value, unit="Gvoxel*exposures/s", cores=cores, kind=kind, sample=sample,
-                seconds_per_pass=sec), result
+                seconds_per_pass=sec, dropin_files=extra), result
 
 
 def run_reference_arm(args):
@@ -343,10 +375,11 @@ def run_b200_arm(args):
         return
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same planes
-    cpu_baseline, parity = None, None
+    cpu_baseline, parity, dropin_files = None, None, None
     if world == 1 and not args.no_cpu:
-        base, ref = cpu_reference_run(args.cpu_nz, 1, 0)
+        base, ref = cpu_reference_run(args.cpu_nz, 1, 0, dropin=True)
         cpu_baseline = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        dropin_files = base.get("dropin_files")
         nv = args.cpu_nz * PLANE
         g_exp = expmap[:nv].cpu().numpy()
         g_dat = out[:nv].cpu().numpy()
@@ -394,6 +427,7 @@ def run_b200_arm(args):
         "gpu_launches": launches[0],
         "clocks": clocks,
         "parity": parity,
+        "dropin_files": dropin_files,
         "rejected_fraction": float(1.0 - n_sel / max(1, int(valid.astype(np.int64).sum()))),
         "exact_fallback_voxels": int(ctools.mpdaf_b200_slow_voxels(local, 0)),
     }

@@ -130,6 +130,11 @@ int mpdaf_b200_last_launch_count(void);
 /* Name of the kernel family the last call dispatched to ("sigclip_reg<48,unit>" ...). */
 const char *mpdaf_b200_last_kernel_name(void);
 
+/* Histogram of the exposure map written by the most recent merging call (hist[k] = number of
+ * voxels combined from k exposures, k = 0 .. nbins-1): the mode over k >= 1 is the `expnb` of
+ * CubeList._compute_expnb (cubelist.py:69-74), obtained on the device instead of a host pass. */
+int mpdaf_b200_last_expmap_histogram(long long *hist, int nbins);
+
 /* Diagnostic: voxels that the certified fast path handed to the exact per-voxel fallback
  * on `device` since the last reset (see DESIGN.md "certified decisions"); -1 if unknown. */
 long long mpdaf_b200_slow_voxels(int device, int reset);

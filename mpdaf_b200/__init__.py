@@ -4,6 +4,6 @@
 behind the same ctypes C ABI as the reference's `_ctools` (src/merging.c),
 implemented as hand-written sm_100a CUDA kernels.  See DESIGN.md.
 """
-from .cubelist import Cube, CubeList, DeviceStack, StatTable  # noqa: F401
+from .cubelist import Cube, CubeList, CubeMosaic, DeviceStack, StatTable  # noqa: F401
 
-__all__ = ['CubeList', 'Cube', 'StatTable', 'DeviceStack']
+__all__ = ['CubeList', 'CubeMosaic', 'Cube', 'StatTable', 'DeviceStack']

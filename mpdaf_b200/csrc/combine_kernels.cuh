@@ -530,6 +530,26 @@ median_generic_kernel(const StackTable* __restrict__ T, const ClipArgs A)
         if (s_valid[i]) atomicAdd(A.valid_cnt + i, (unsigned long long)s_valid[i]);
 }
 
+// Histogram of the exposure map (how many voxels were built from 0, 1, ... N exposures): what
+// CubeList._compute_expnb (cubelist.py:69-74) needs, without a host pass over the whole map.
+__global__ void expmap_hist_kernel(const int* __restrict__ expmap, long long n, unsigned long long* __restrict__ hist)
+{
+    __shared__ unsigned s_hist[kGenericMax + 1];
+    for (int i = threadIdx.x; i <= kGenericMax; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int e = __ldcs(expmap + i);
+        // most voxels of a warp share one value: aggregate before touching shared memory
+        const unsigned peers = __match_any_sync(__activemask(), e);
+        if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31) && e >= 0 && e <= kGenericMax)
+            atomicAdd(&s_hist[e], (unsigned)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= kGenericMax; i += blockDim.x)
+        if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
+}
+
 // In-place byte swap of big-endian float32 samples staged from a FITS HDU.
 __global__ void bswap32_kernel(uint32_t* __restrict__ p, long long n)
 {

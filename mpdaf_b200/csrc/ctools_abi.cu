@@ -32,6 +32,8 @@ using namespace mb;
 thread_local std::string g_error;
 std::mutex g_call_mutex;              // one merging call at a time (ctools.py contract)
 double g_last_kernel_ms = 0.0;
+unsigned long long g_last_hist[kGenericMax + 1];
+bool g_hist_enabled = true;
 int g_last_launches = 0;
 std::string g_last_kernel = "none";
 
@@ -58,6 +60,7 @@ struct DeviceState {
     unsigned long long* counters = nullptr;  // [2][kGenericMax]: valid, select
     StackTable* table = nullptr;             // device copy for the generic kernels
     unsigned long long* slow = nullptr;      // voxels recomputed by the exact fallback (diagnostic)
+    unsigned long long* hist = nullptr;      // [kGenericMax + 1] exposure-map histogram of the last call
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 DeviceState g_dev[16];
@@ -80,6 +83,7 @@ int device_ready(int device)
     MB_CUDA(cudaMalloc(&d.table, sizeof(StackTable)));
     MB_CUDA(cudaMalloc(&d.slow, sizeof(unsigned long long)));
     MB_CUDA(cudaMemset(d.slow, 0, sizeof(unsigned long long)));
+    MB_CUDA(cudaMalloc(&d.hist, (kGenericMax + 1) * sizeof(unsigned long long)));
     MB_CUDA(cudaEventCreate(&d.ev0));
     MB_CUDA(cudaEventCreate(&d.ev1));
     d.ready = true;
@@ -287,8 +291,22 @@ int launch_generic(const Job& j, int device, cudaStream_t stream)
                              (const StackTable*)j.table_dev, j.a);
 }
 
-// Enqueue the combination of one device-resident stack (or slab) on `stream`.
+int enqueue_combine_only(const Job& j, int device, cudaStream_t stream);
+
+// Enqueue the combination of one device-resident stack (or slab) on `stream`, followed by the
+// exposure-map histogram of that slab (expnb without a host pass).
 int enqueue_combine(const Job& j, int device, cudaStream_t stream)
+{
+    const int rc = enqueue_combine_only(j, device, stream);
+    if (rc != MPDAF_B200_OK || !g_hist_enabled || j.a.nvox <= 0) return rc;
+    const int grid = (int)std::min<long long>((j.a.nvox + 255) / 256, (long long)g_dev[device].sm_count * 8);
+    expmap_hist_kernel<<<grid, 256, 0, stream>>>(j.a.expmap, j.a.nvox, g_dev[device].hist);
+    MB_CUDA(cudaGetLastError());
+    g_last_launches++;
+    return MPDAF_B200_OK;
+}
+
+int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
 {
     bool unit = true;
     for (int i = 0; i < j.nfiles; i++) {
@@ -585,6 +603,9 @@ int run_job(Job job, const SlabSource* slab_src, int location, int device, doubl
 
     cudaStream_t cstream = (location == MPDAF_B200_DEVICE) ? stream : nullptr;
     MB_CUDA(cudaMemsetAsync(d.counters, 0, 2 * kGenericMax * sizeof(unsigned long long), cstream));
+    MB_CUDA(cudaMemsetAsync(d.hist, 0, (kGenericMax + 1) * sizeof(unsigned long long), cstream));
+    static const bool hist_off = std::getenv("MPDAF_B200_NO_HISTOGRAM") != nullptr;
+    g_hist_enabled = !hist_off;
     if (location == MPDAF_B200_DEVICE) {
         job.table_dev = d.table;
         job.a.out = out;
@@ -605,6 +626,7 @@ int run_job(Job job, const SlabSource* slab_src, int location, int device, doubl
     }
     unsigned long long host_counts[2 * kGenericMax];
     MB_CUDA(cudaMemcpyAsync(host_counts, d.counters, sizeof host_counts, cudaMemcpyDeviceToHost, cstream));
+    MB_CUDA(cudaMemcpyAsync(g_last_hist, d.hist, sizeof g_last_hist, cudaMemcpyDeviceToHost, cstream));
     MB_CUDA(cudaStreamSynchronize(cstream));
     if (location == MPDAF_B200_DEVICE && job.a.nvox > 0) {
         float ms = 0.f;
@@ -801,6 +823,13 @@ int mpdaf_b200_median_arrays(int nfiles, const void* const* data, int elem_type,
 }
 
 double mpdaf_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
+
+int mpdaf_b200_last_expmap_histogram(long long* hist, int nbins)
+{
+    if (!hist || nbins < 1) return MPDAF_B200_ERR_ARG;
+    for (int i = 0; i < nbins; i++) hist[i] = i <= kGenericMax ? (long long)g_last_hist[i] : 0;
+    return MPDAF_B200_OK;
+}
 
 long long mpdaf_b200_slow_voxels(int device, int reset)
 {

@@ -86,6 +86,9 @@ else:
     ctools.mpdaf_b200_last_kernel_name.argtypes = []
     ctools.mpdaf_b200_last_error.restype = ctypes.c_char_p
     ctools.mpdaf_b200_last_error.argtypes = []
+    ctools.mpdaf_b200_last_expmap_histogram.restype = ctypes.c_int
+    ctools.mpdaf_b200_last_expmap_histogram.argtypes = [ndpointer(dtype=ctypes.c_longlong, ndim=1, flags='C_CONTIGUOUS'),
+                                                        ctypes.c_int]
     ctools.mpdaf_b200_slow_voxels.restype = ctypes.c_longlong
     ctools.mpdaf_b200_slow_voxels.argtypes = [ctypes.c_int, ctypes.c_int]
     ctools.mpdaf_b200_device_count.restype = ctypes.c_int

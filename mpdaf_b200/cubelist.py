@@ -27,7 +27,7 @@ import numpy as np
 
 from . import fits as _fits
 
-__all__ = ('CubeList', 'Cube', 'StatTable', 'DeviceStack')
+__all__ = ('CubeList', 'CubeMosaic', 'Cube', 'StatTable', 'DeviceStack')
 
 __version__ = '0.1'
 
@@ -58,6 +58,16 @@ def _compute_expnb(expmap):
     if counts.size <= 1 or counts[1:].max() == 0:
         return 0
     return int(np.argmax(counts[1:])) + 1
+
+
+def _expnb_from_device(nfiles):
+    """expnb from the exposure-map histogram the library accumulated on the device during the
+    merging call just made; same tie rule as `_compute_expnb`."""
+    from .ctools import ctools
+    hist = np.zeros(nfiles + 1, dtype=np.int64)
+    if ctools.mpdaf_b200_last_expmap_histogram(hist, nfiles + 1) != 0 or hist[1:].max(initial=0) == 0:
+        return None
+    return int(np.argmax(hist[1:])) + 1
 
 
 def _add_method_keywords(header, method, params, values, comments):
@@ -338,7 +348,9 @@ class CubeList:
         no_valid_pix = npixels - valid_pix
         stat_pix = StatTable([self.files, no_valid_pix], names=['FILENAME', 'NPIX_NAN'])
 
-        kwargs = dict(expnb=_compute_expnb(expmap), method='obj.cubelist.median', header=header)
+        expnb = _expnb_from_device(self.nfiles)
+        kwargs = dict(expnb=_compute_expnb(expmap) if expnb is None else expnb,
+                      method='obj.cubelist.median', header=header)
         expmap = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
         cube = self.save_combined_cube(data, **kwargs)
         return cube, expmap, stat_pix
@@ -414,11 +426,66 @@ class CubeList:
                     ('nclip_up', nclip_up, 'upper clipping parameter'),
                     ('nstop', nstop, 'clipping minimum number'),
                     ('var', var, 'type of variance')]
-        kwargs = dict(expnb=_compute_expnb(expmap), keywords=keywords, header=header,
+        expnb = _expnb_from_device(self.nfiles)
+        kwargs = dict(expnb=_compute_expnb(expmap) if expnb is None else expnb, keywords=keywords, header=header,
                       method='obj.cubelist.merging')
         expmap = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
         cube = self.save_combined_cube(data, var=vardata, **kwargs)
         return cube, expmap, statpix
+
+    # ------------------------------------------------------------------
+    # The reference's "py" route (cubelist.py:77-216, :538-576; merging.pyx:61-125): same statistics,
+    # optional per-cube (y, x) placement inside a larger output grid, and a `rejmap` output.  Here it
+    # is the same CUDA path fed with NaN-padded exposures; `rejmap` = valid samples - expmap.
+    def _placed_exposures(self, extname, nl, pos, shapes):
+        nz, ny, nx = self.shape
+        nl = nz if nl is None else int(nl)
+        out = []
+        for i, f in enumerate(self.files):
+            img = _fits.read_image(f, extname)
+            if pos is None and img.shape[1:] == (ny, nx):
+                out.append(np.ascontiguousarray(img[:nl], dtype=np.float32))
+                continue
+            arr = np.full((nl, ny, nx), np.nan, dtype=np.float32)
+            y0, x0 = (0, 0) if pos is None else (int(pos[i][0]), int(pos[i][1]))
+            sy, sx = img.shape[1:] if shapes is None else (int(shapes[i][0]), int(shapes[i][1]))
+            ys, xs = max(y0, 0), max(x0, 0)
+            ye, xe = min(y0 + sy, ny), min(x0 + sx, nx)
+            if ye > ys and xe > xs:
+                arr[:, ys:ye, xs:xe] = img[:nl, ys - y0:ye - y0, xs - x0:xe - x0]
+            out.append(arr)
+        return out, nl
+
+    def _pycombine(self, nmax=2, nclip=5.0, var='propagate', nstop=2, nl=None, header=None, mad=False,
+                   pos=None, shapes=None, method='obj.cubelist.pycombine'):
+        data, nl = self._placed_exposures('DATA', nl, pos, shapes)
+        stat = self._placed_exposures('STAT', nl, pos, shapes)[0] if var == 'propagate' else None
+        shape = (nl,) + tuple(self.shape[1:])
+        inner = CubeList.from_arrays(data, stat, scalelist=self.flux_scales, offsetlist=self.flux_offsets,
+                                     names=self.files)
+        inner._headers = self._headers
+        inner.unit = self.unit
+        cube, expmap, stat_pix = inner.combine(nmax=nmax, nclip=nclip, nstop=nstop, var=var, mad=mad, header=header)
+        nvalid = np.zeros(shape, dtype=np.int32)
+        for d in data:
+            nvalid += ~np.isnan(d)
+        rejmap_data = (nvalid - expmap.data).astype(np.int32)
+        for c in (cube, expmap):
+            for key in list(c.primary_header):
+                if key.startswith('HIERARCH MPDAF METH') and key.endswith(' ID'):
+                    c.primary_header[key] = (method, 'MPDAF method identifier')
+        rejmap = Cube(rejmap_data, primary_header=expmap.primary_header, data_header=expmap.data_header,
+                      unit='dimensionless', comments=expmap.comments)
+        return cube, expmap, stat_pix, rejmap
+
+    def pycombine(self, nmax=2, nclip=5.0, var='propagate', nstop=2, nl=None, header=None, mad=False):
+        """`CubeList.combine` with the reference's pycombine signature and 4-tuple return
+        (cube, expmap, statpix, rejmap) (cubelist.py:572-576)."""
+        return self._pycombine(nmax=nmax, nclip=nclip, var=var, nstop=nstop, nl=nl, header=header, mad=mad)
+
+    def pymedian(self, header=None):
+        """Same result as `median` (the reference's python-fitsio route, cubelist.py:538-570)."""
+        return self.median(header=header)
 
     # ------------------------------------------------------------------
     def _run_device_stack(self, median, valid_pix, select_pix, scale=None, offset=None, params=None):
@@ -447,3 +514,53 @@ class CubeList:
             scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix, *params, stream)
         check(rc, 'mpdaf_b200_sigma_clipping_arrays')
         return out.cpu().numpy(), outvar.cpu().numpy(), expmap.cpu().numpy()
+
+
+class CubeMosaic(CubeList):
+
+    """Manages a list of cubes and handles the combination to make a mosaic.
+
+    Same contract as the reference (cubelist.py:582-705): all cubes share one WCS grid, the
+    ``CRPIX`` keywords give each cube's integer offset inside the output grid, whose shape comes
+    from the ``output_wcs`` FITS cube.  Only `pycombine` is available.
+    """
+
+    def __init__(self, files, output_wcs, **kwargs):
+        hdus = _fits.read_hdus(output_wcs)
+        self._out_header = next(h for h, _, _ in hdus if str(h.get('EXTNAME', '')).upper() == 'DATA')
+        super().__init__(files, **kwargs)
+
+    def _set_defaults(self):
+        h = self._out_header
+        self.shape = (int(h['NAXIS3']), int(h['NAXIS2']), int(h['NAXIS1']))
+        self.unit = h.get('BUNIT')
+
+    def check_dim(self):
+        """Checks if all cubes have the same spectral range."""
+        nz = {int(h['NAXIS3']) for _, h in self._headers}
+        assert len(nz) == 1, 'Cubes must have the same spectral range.'
+        return True
+
+    def __getitem__(self, item):
+        raise ValueError('Operation forbidden')
+
+    def combine(self):
+        """This method is not implemented for CubeMosaic."""
+        raise NotImplementedError
+
+    def median(self):
+        """This method is not implemented for CubeMosaic."""
+        raise NotImplementedError
+
+    def pymedian(self):
+        """This method is not implemented for CubeMosaic."""
+        raise NotImplementedError
+
+    def pycombine(self, nmax=2, nclip=5.0, var='propagate', nstop=2, nl=None, header=None, mad=False):
+        def crpix(h):   # (CRPIX2, CRPIX1): python (y, x) order, cubelist.py:697-699
+            return np.array([float(h.get('CRPIX2', 1.0)), float(h.get('CRPIX1', 1.0))])
+        out = crpix(self._out_header)
+        pos = np.array([np.rint(out - crpix(h)) for _, h in self._headers], dtype=int)
+        shapes = np.array([(int(h['NAXIS2']), int(h['NAXIS1'])) for _, h in self._headers])
+        return self._pycombine(nmax=nmax, nclip=nclip, var=var, nstop=nstop, nl=nl, header=header, mad=mad,
+                               pos=pos, shapes=shapes, method='obj.cubemosaic.pycombine')
