@@ -2,26 +2,29 @@
 
 In-tree build with nvcc for sm_100a only; the .so is git-ignored but travels to
 the GPU box with the repository snapshot.  `python -m mpdaf_b200.build` or
-`__graft_entry__.build()`.
+`__graft_entry__.build()`.  The kernels are split into one translation unit per
+stack-depth bucket (warp_<NB>.cu) so that they compile in parallel.
 """
 import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "_ctools.so")
-SOURCES = ("ctools_abi.cu", "fits_reader.cpp", "host_tools.cpp")
-DEPS = SOURCES + ("combine_kernels.cuh", "sigclip_tile.cuh", "sigclip_warp.cuh", "sort_networks.cuh", "synth_core.h", "fits_reader.h",
-                  os.path.join("..", "..", "include", "mpdaf_b200.h"))
+DEPTHS = (4, 8, 12, 16, 24, 32, 48, 64, 96, 128)
+SOURCES = ("ctools_abi.cu", "fits_reader.cpp", "host_tools.cpp") + tuple(f"warp_{n}.cu" for n in DEPTHS)
+HEADERS = ("combine_kernels.cuh", "sigclip_tile.cuh", "sigclip_warp.cuh", "warp_inst.cuh", "launch.h",
+           "sort_networks.cuh", "synth_core.h", "fits_reader.h", os.path.join("..", "..", "include", "mpdaf_b200.h"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",                       # no FMA contraction in the float64 statistics
     "-Xcompiler", "-fPIC,-ffp-contract=off,-pthread",
-    "-shared",
 ]
 
 
@@ -32,29 +35,52 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def _newest_header():
+    return max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
+
+
 def is_stale():
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    t = _mtime(LIB)
+    return t == 0.0 or any(_mtime(os.path.join(CSRC, s)) > t for s in SOURCES) or _newest_header() > t
 
 
-def build_library(force=False, verbose=False):
-    """Compile the library if a source is newer than the .so.  Returns its path."""
-    if not force and not is_stale():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + list(SOURCES)
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd))
-    env = dict(os.environ)
-    env.setdefault("PATH", "")
-    res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+def build_library(force=False, verbose=False, extra_flags=(), lib=LIB):
+    """Compile what is out of date and link the library.  Returns its path."""
+    if not force and not extra_flags and lib == LIB and not is_stale():
+        return lib
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+    hdr_t = _newest_header()
+    tag = "".join(c if c.isalnum() else "_" for c in "".join(extra_flags))
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(OBJ, os.path.splitext(src)[0] + tag + ".o")
+        if force or _mtime(obj) < max(_mtime(os.path.join(CSRC, src)), hdr_t):
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            jobs.append((src, cmd))
+
+    def run(job):
+        src, cmd = job
+        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        return src, res
+
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 4))) as pool:
+        for src, res in pool.map(run, jobs):
+            if verbose or res.returncode != 0:
+                sys.stderr.write(f"--- {src}\n{res.stdout}{res.stderr}")
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}")
+    objs = [os.path.join(OBJ, os.path.splitext(s)[0] + tag + ".o") for s in SOURCES]
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib] + objs,
+                         cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed building _ctools.so")
-    return LIB
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("linking _ctools.so failed")
+    return lib
 
 
 if __name__ == "__main__":

@@ -532,7 +532,7 @@ median_generic_kernel(const StackTable* __restrict__ T, const ClipArgs A)
 
 // Histogram of the exposure map (how many voxels were built from 0, 1, ... N exposures): what
 // CubeList._compute_expnb (cubelist.py:69-74) needs, without a host pass over the whole map.
-__global__ void expmap_hist_kernel(const int* __restrict__ expmap, long long n, unsigned long long* __restrict__ hist)
+static __global__ void expmap_hist_kernel(const int* __restrict__ expmap, long long n, unsigned long long* __restrict__ hist)
 {
     __shared__ unsigned s_hist[kGenericMax + 1];
     for (int i = threadIdx.x; i <= kGenericMax; i += blockDim.x) s_hist[i] = 0u;
@@ -551,14 +551,14 @@ __global__ void expmap_hist_kernel(const int* __restrict__ expmap, long long n, 
 }
 
 // In-place byte swap of big-endian float32 samples staged from a FITS HDU.
-__global__ void bswap32_kernel(uint32_t* __restrict__ p, long long n)
+static __global__ void bswap32_kernel(uint32_t* __restrict__ p, long long n)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         p[i] = __byte_perm(p[i], 0, 0x0123);
 }
 
-__global__ void bswap64_kernel(unsigned long long* __restrict__ p, long long n)
+static __global__ void bswap64_kernel(unsigned long long* __restrict__ p, long long n)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {

@@ -18,10 +18,8 @@
 
 #include <cuda_runtime.h>
 
-#include "../../include/mpdaf_b200.h"
-#include "combine_kernels.cuh"
+#include "launch.h"
 #include "sigclip_tile.cuh"
-#include "sigclip_warp.cuh"
 #include "fits_reader.h"
 #include "synth_core.h"
 
@@ -37,19 +35,17 @@ bool g_hist_enabled = true;
 int g_last_launches = 0;
 std::string g_last_kernel = "none";
 
-int fail(int code, const std::string& msg)
+}  // namespace
+
+int mb::fail(int code, const std::string& msg)
 {
     g_error = msg;
     std::fprintf(stderr, "mpdaf_b200: %s\n", msg.c_str());
     return code;
 }
 
-#define MB_CUDA(call)                                                                     \
-    do {                                                                                  \
-        cudaError_t e_ = (call);                                                          \
-        if (e_ != cudaSuccess)                                                            \
-            return fail(MPDAF_B200_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
-    } while (0)
+namespace {
+using mb::fail;
 
 // ---------------------------------------------------------------------------
 // per-device state
@@ -93,18 +89,6 @@ int device_ready(int device)
 // ---------------------------------------------------------------------------
 // kernel selection
 // ---------------------------------------------------------------------------
-struct Job {
-    int nfiles = 0;
-    int elem = MPDAF_B200_F32;
-    bool median = false;
-    const void* const* data = nullptr;  // host table of DEVICE pointers
-    const void* const* var = nullptr;
-    const double* scale = nullptr;       // host, may be null
-    const double* offset = nullptr;
-    StackTable* table_dev = nullptr;     // device scratch for the generic kernels' stack table
-    ClipArgs a{};
-};
-
 int bucket_of(int nfiles)
 {
     const int sizes[] = {4, 8, 12, 16, 24, 32, 48, 64, 96, 128};
@@ -194,77 +178,6 @@ int launch_tile(const Job& j, bool unit, int device, cudaStream_t stream)
     return launch(sigclip_tile_kernel<NB, false>);
 }
 
-// Warp-tiled sigma clip (sigclip_warp.cuh): the main kernel for float32 stacks up to 64 deep.
-template <int NB>
-int launch_warp(const Job& j, bool unit, int device, cudaStream_t stream)
-{
-    TileArgs<NB> s;
-    for (int i = 0; i < NB; i++) {
-        const bool in = i < j.nfiles;
-        s.data[i] = in ? static_cast<const float*>(j.data[i]) : nullptr;
-        s.var[i] = (in && j.var) ? static_cast<const float*>(j.var[i]) : nullptr;
-        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
-        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
-        s.scale2[i] = s.scale[i] * s.scale[i];
-    }
-    char name[64];
-    std::snprintf(name, sizeof name, "sigclip_warp<%d,%s>", NB, unit ? "unit" : "scaled");
-    g_last_kernel = name;
-    auto launch = [&](auto kernel, long long t0, long long t1) -> int {
-        if (t1 <= t0) return MPDAF_B200_OK;
-        const int smem = (int)sizeof(BlockSmem<NB>);
-        MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int per_sm = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWT, smem));
-        if (per_sm < 1) per_sm = 1;
-        const long long nblocks = (t1 - t0 + (kWT / 32) - 1) / (kWT / 32);
-        const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-        static const int flags = std::getenv("MPDAF_B200_WARP_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : (NB >= 24 ? 1 : 0);
-        kernel<<<grid, kWT, smem, stream>>>(s, j.a, t0, t1, flags, g_dev[device].slow);
-        MB_CUDA(cudaGetLastError());
-        g_last_launches++;
-        return MPDAF_B200_OK;
-    };
-    const long long ntiles = (j.a.nvox + 31) / 32;
-    if (unit) return launch(sigclip_warp_kernel<NB, true, 0>, 0, ntiles);
-    return launch(sigclip_warp_kernel<NB, false, 0>, 0, ntiles);
-}
-
-template <int NB>
-int launch_median_warp(const Job& j, int device, cudaStream_t stream)
-{
-    TileArgs<NB> s;
-    for (int i = 0; i < NB; i++) {
-        s.data[i] = i < j.nfiles ? static_cast<const float*>(j.data[i]) : nullptr;
-        s.var[i] = nullptr;
-        s.scale[i] = 1.0;
-        s.offset[i] = 0.0;
-        s.scale2[i] = 1.0;
-    }
-    char name[64];
-    std::snprintf(name, sizeof name, "median_warp<%d>", NB);
-    g_last_kernel = name;
-    static const int sort_reps = std::getenv("MPDAF_B200_SORT_REPS") ? std::atoi(std::getenv("MPDAF_B200_SORT_REPS")) : 1;
-    static const int fma_every = std::getenv("MPDAF_B200_FMA_EVERY") ? std::atoi(std::getenv("MPDAF_B200_FMA_EVERY")) : 1;
-    auto launch = [&](auto kernel) -> int {
-        int per_sm = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
-        if (per_sm < 1) per_sm = 1;
-        const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
-        const int grid = (int)std::max(1LL, std::min(nblocks, (long long)g_dev[device].sm_count * per_sm));
-        kernel<<<grid, kThreads, 0, stream>>>(s, j.a, sort_reps);
-        MB_CUDA(cudaGetLastError());
-        g_last_launches++;
-        return MPDAF_B200_OK;
-    };
-    if constexpr (NB == 12 || NB == 48) {
-        if (fma_every == 0) return launch(median_warp_kernel<NB, 0>);
-        if (fma_every == 2) return launch(median_warp_kernel<NB, 2>);
-        if (fma_every == 3) return launch(median_warp_kernel<NB, 3>);
-    }
-    return launch(median_warp_kernel<NB, 1>);
-}
-
 template <int MAXN, typename ElemT>
 int launch_generic(const Job& j, int device, cudaStream_t stream)
 {
@@ -317,33 +230,23 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
     const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32 && (j.median || !j.a.mad);
     static const std::string which = std::getenv("MPDAF_B200_KERNEL") ? std::getenv("MPDAF_B200_KERNEL") : "warp";
     const bool use_v1 = which == "reg";
-    if (reg_ok && !j.median && which == "warp") {
+    if (reg_ok && which == "warp") {
+        char name[64] = "";
+        LaunchCtx ctx;
+        ctx.sm_count = g_dev[device].sm_count;
+        ctx.slow = g_dev[device].slow;
+        ctx.stream = stream;
+        ctx.name = name;
+        ctx.name_len = sizeof name;
+        int rc = MPDAF_B200_ERR_ARG;
         switch (nb) {
-            case 4: return launch_warp<4>(j, unit, device, stream);
-            case 8: return launch_warp<8>(j, unit, device, stream);
-            case 12: return launch_warp<12>(j, unit, device, stream);
-            case 16: return launch_warp<16>(j, unit, device, stream);
-            case 24: return launch_warp<24>(j, unit, device, stream);
-            case 32: return launch_warp<32>(j, unit, device, stream);
-            case 48: return launch_warp<48>(j, unit, device, stream);
-            case 64: return launch_warp<64>(j, unit, device, stream);
-            case 96: return launch_warp<96>(j, unit, device, stream);
-            case 128: return launch_warp<128>(j, unit, device, stream);
+#define MB_CASE(NB) case NB: rc = j.median ? mb_launch_median_warp_##NB(j, ctx) : mb_launch_warp_##NB(j, unit, ctx); break;
+            MB_FOR_EACH_DEPTH(MB_CASE)
+#undef MB_CASE
         }
-    }
-    if (reg_ok && j.median && which == "warp") {
-        switch (nb) {
-            case 4: return launch_median_warp<4>(j, device, stream);
-            case 8: return launch_median_warp<8>(j, device, stream);
-            case 12: return launch_median_warp<12>(j, device, stream);
-            case 16: return launch_median_warp<16>(j, device, stream);
-            case 24: return launch_median_warp<24>(j, device, stream);
-            case 32: return launch_median_warp<32>(j, device, stream);
-            case 48: return launch_median_warp<48>(j, device, stream);
-            case 64: return launch_median_warp<64>(j, device, stream);
-            case 96: return launch_median_warp<96>(j, device, stream);
-            case 128: return launch_median_warp<128>(j, device, stream);
-        }
+        g_last_kernel = name;
+        g_last_launches += ctx.launches;
+        return rc;
     }
     if (reg_ok && !j.median && !use_v1) {
         switch (nb) {

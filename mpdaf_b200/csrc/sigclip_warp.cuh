@@ -278,7 +278,9 @@ struct TransposeConsts {
 // resident 128-thread blocks per SM each depth is compiled for (register budget 65536 / (128 * blocks))
 template <int NB> struct WarpBlocks { static constexpr int value = (NB <= 64 ? MB_WARP_BLOCKS : (NB <= 96 ? 3 : 2)) * 128 / kWT; };
 
-template <int NB, bool UNIT, int FMA_EVERY>
+// FULL: every exposure slot is in use (nfiles == NB), so the per-row `i < nfiles` predicates and
+// selects compile away (the common case: depths 4, 8, 12, 16, 24, 32, 48, 64, 96, 128).
+template <int NB, bool UNIT, bool FULL>
 __global__ void __launch_bounds__(kWT, WarpBlocks<NB>::value)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
                     const int flags, unsigned long long* slow_total)
@@ -293,11 +295,9 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int wib = tid >> 5;
-    const int nfiles = A.nfiles;
+    const int nfiles = FULL ? NB : A.nfiles;
     const int nstop = A.nstop < 1 ? 1 : A.nstop;
     const bool want_var = (A.typ_var == 0);
-    const unsigned one = (unsigned)(A.nfiles > 0);           // opaque 1 / -1 for the IMAD form
-    const unsigned minus_one = 0u - one;
 
     for (int i = tid; i < NB; i += kWT) {
         sm.scale[i] = S.scale[i];
@@ -392,7 +392,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         }
         const int n = NB - inval.count();
 
-        sort_keys_mixed<NB, FMA_EVERY>(key, one, minus_one);
+        sort_keys_mixed<NB, 0>(key, 0u, 0u);
 #pragma unroll
         for (int q = 0; q < NB; q++) sk[q][lane] = key[q];
 
@@ -570,12 +570,12 @@ namespace mb {
 // of this kernel -- measured: FMNMX 64 lanes/clk/SM, IADD3 more than that, IMAD 64, so the plain
 // FMNMX + IADD3 form sustains ~60 compare-exchanges/clk/SM, twice the 2xIMAD form); per-exposure valid counts come from one 32x32 bit transpose per 32 exposures.
 // ---------------------------------------------------------------------------------------------
-template <int NB, int FMA_EVERY>
-__global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const int sort_reps)
+template <int NB, bool FULL>
+__global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A)
 {
     constexpr int W = ExpSet<NB>::W;
     const int lane = threadIdx.x & 31;
-    const int nfiles = A.nfiles;
+    const int nfiles = FULL ? NB : A.nfiles;
     const unsigned one = (unsigned)(A.nfiles > 0);
     const unsigned minus_one = 0u - one;
     TransposeConsts tc;
@@ -610,9 +610,7 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
             }
         }
         const int n = NB - inval.count();
-#pragma unroll 1
-        for (int rep = 0; rep < sort_reps; rep++)   // sort_reps > 1: instruction-cache experiment only
-            sort_keys_mixed<NB, FMA_EVERY>(key, one, minus_one);
+        sort_keys_mixed<NB, 1>(key, one, minus_one);   // 2xIMAD form: measured a few % faster here
         // first invalid sample went to +inf: with an odd number of them there is one more +inf than
         // -inf, so the valid samples occupy slots [a, a+n) with a = floor((NB-n)/2) and the middle
         // of the valid run is at slot NB/2-1 (odd n) or slots NB/2-1, NB/2 (even n)

@@ -1,0 +1,3 @@
+// Warp-tiled kernels for stacks of up to 64 exposures (one translation unit per depth bucket).
+#include "warp_inst.cuh"
+MB_DEFINE_DEPTH(64)

@@ -1,0 +1,77 @@
+// Launchers of the warp-tiled kernels for one stack-depth bucket; included by warp_<NB>.cu.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "launch.h"
+#include "sigclip_warp.cuh"
+
+namespace mb {
+
+template <int NB>
+void fill_tile_args(TileArgs<NB>& s, const Job& j)
+{
+    for (int i = 0; i < NB; i++) {
+        const bool in = i < j.nfiles;
+        s.data[i] = in ? static_cast<const float*>(j.data[i]) : nullptr;
+        s.var[i] = (in && j.var) ? static_cast<const float*>(j.var[i]) : nullptr;
+        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
+        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
+        s.scale2[i] = s.scale[i] * s.scale[i];
+    }
+}
+
+// Warp-tiled sigma clip (sigclip_warp.cuh): the main kernel for float32 stacks up to 128 deep.
+template <int NB>
+int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
+{
+    TileArgs<NB> s;
+    fill_tile_args(s, j);
+    const bool full = (j.nfiles == NB);   // every slot in use: the per-row predicates compile away
+    std::snprintf(ctx.name, ctx.name_len, "sigclip_warp<%d,%s%s>", NB, unit ? "unit" : "scaled", full ? "" : ",partial");
+    static const int flags = std::getenv("MPDAF_B200_WARP_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : (NB >= 24 ? 1 : 0);
+    auto launch = [&](auto kernel) -> int {
+        const int smem = (int)sizeof(BlockSmem<NB>);
+        MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWT, smem));
+        if (per_sm < 1) per_sm = 1;
+        const long long ntiles = (j.a.nvox + 31) / 32;
+        const long long nblocks = (ntiles + (kWT / 32) - 1) / (kWT / 32);
+        const int grid = (int)std::max(1LL, std::min(nblocks, (long long)ctx.sm_count * per_sm));
+        kernel<<<grid, kWT, smem, ctx.stream>>>(s, j.a, 0LL, ntiles, flags, ctx.slow);
+        MB_CUDA(cudaGetLastError());
+        ctx.launches++;
+        return MPDAF_B200_OK;
+    };
+    if (unit) return full ? launch(sigclip_warp_kernel<NB, true, true>) : launch(sigclip_warp_kernel<NB, true, false>);
+    return full ? launch(sigclip_warp_kernel<NB, false, true>) : launch(sigclip_warp_kernel<NB, false, false>);
+}
+
+template <int NB>
+int launch_median_warp_impl(const Job& j, LaunchCtx& ctx)
+{
+    TileArgs<NB> s;
+    fill_tile_args(s, j);
+    const bool full = (j.nfiles == NB);
+    std::snprintf(ctx.name, ctx.name_len, "median_warp<%d%s>", NB, full ? "" : ",partial");
+    auto launch = [&](auto kernel) -> int {
+        int per_sm = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        const long long nblocks = ((j.a.nvox + 31) / 32 + (kThreads / 32) - 1) / (kThreads / 32);
+        const int grid = (int)std::max(1LL, std::min(nblocks, (long long)ctx.sm_count * per_sm));
+        kernel<<<grid, kThreads, 0, ctx.stream>>>(s, j.a);
+        MB_CUDA(cudaGetLastError());
+        ctx.launches++;
+        return MPDAF_B200_OK;
+    };
+    return full ? launch(median_warp_kernel<NB, true>) : launch(median_warp_kernel<NB, false>);
+}
+
+}  // namespace mb
+
+#define MB_DEFINE_DEPTH(NB)                                                                                   \
+    int mb_launch_warp_##NB(const mb::Job& j, bool unit, mb::LaunchCtx& ctx) { return mb::launch_warp_impl<NB>(j, unit, ctx); } \
+    int mb_launch_median_warp_##NB(const mb::Job& j, mb::LaunchCtx& ctx) { return mb::launch_median_warp_impl<NB>(j, ctx); }
