@@ -587,6 +587,7 @@ __global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB
 
     const long long ntiles = (A.nvox + 31) >> 5;
     const long long wstride = (long long)gridDim.x * (kThreads / 32);
+    // (no per-tile phase lock here: measured 8 % slower for the median, unlike the sigma clip)
     for (long long tile = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
         const long long v = (tile << 5) + lane;
         const bool act = v < A.nvox;
