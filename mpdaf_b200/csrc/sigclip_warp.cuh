@@ -392,9 +392,11 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         }
         const int n = NB - inval.count();
 
+        if (!(flags & 4)) {   // flags & 4: timing experiment only (skips the sort and the clip loop; wrong results)
         sort_keys_mixed<NB, 0>(key, 0u, 0u);
 #pragma unroll
         for (int q = 0; q < NB; q++) sk[q][lane] = key[q];
+        }
 
         // STAT rows: issued now, into the registers the keys just vacated, consumed after the clip
         // loop -- their latency hides behind it.  Unconditional loads: rows beyond nfiles alias
@@ -413,7 +415,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         int a = 0, b = n;
         ExpSet<NB> rejected;
         bool slow = false;
-        if (n >= 2) {
+        if (n >= 2 && !(flags & 4)) {
             const double S2_0 = S2;
             int it = A.nmax;
             // values beyond float range or an absurd pivot defeat the key precision model
