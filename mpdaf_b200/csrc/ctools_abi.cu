@@ -227,7 +227,7 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         if (j.offset && j.offset[i] != 0.0) unit = false;
     }
     const int nb = bucket_of(j.nfiles);
-    const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32 && (j.median || !j.a.mad);
+    const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32;
     static const std::string which = std::getenv("MPDAF_B200_KERNEL") ? std::getenv("MPDAF_B200_KERNEL") : "warp";
     const bool use_v1 = which == "reg";
     if (reg_ok && which == "warp") {

@@ -94,13 +94,14 @@ struct WarpSmem {
 
 constexpr int kWT = MB_WARP_THREADS;
 
-template <int NB>
+template <int NB, bool MAD = false>
 struct BlockSmem {
     WarpSmem<NB> w[kWT / 32];
     double scale[NB];
     double offset[NB];
     double rcp[NB + 1];   // 1.0 / m
     const float* data[NB];   // exposure base pointers (lane-dependent lookups of rejected samples)
+    double sw[MAD ? kWT / 32 : 1][MAD ? NB : 1][32];   // MAD: exact w in ascending order, one column per lane
 };
 
 // compare-exchange variants: the max as a + b - min on the ALU (IADD3) or on the FMA pipe (2 IMAD)
@@ -280,13 +281,21 @@ template <int NB> struct WarpBlocks { static constexpr int value = (NB <= 64 ? M
 
 // FULL: every exposure slot is in use (nfiles == NB), so the per-row `i < nfiles` predicates and
 // selects compile away (the common case: depths 4, 8, 12, 16, 24, 32, 48, 64, 96, 128).
-template <int NB, bool UNIT, bool FULL>
+//
+// MAD (tools.c:122-158, :54-77): sigma = 1.4826 * median(|w - median(w)|).  The sorted keys give the
+// order of the samples up to key-bucket ties; the exact float64 values are then written in that
+// order to a second shared-memory column (ties repaired by a local insertion), and from there the
+// reference algorithm runs literally: exact medians, the MAD as the middle of the two sorted runs
+// of absolute deviations left and right of the median (outward merge), exact strict window counts
+// by binary search on the float64 column, ascending-order sums for the later means.  No error
+// bounds are involved in this mode: every output is the reference's, bit for bit.
+template <int NB, bool UNIT, bool FULL, bool MAD = false>
 __global__ void __launch_bounds__(kWT, WarpBlocks<NB>::value)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
                     const int flags, unsigned long long* slow_total)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BlockSmem<NB>& sm = *reinterpret_cast<BlockSmem<NB>*>(smem_raw);
+    BlockSmem<NB, MAD>& sm = *reinterpret_cast<BlockSmem<NB, MAD>*>(smem_raw);
     constexpr int W = ExpSet<NB>::W;
     constexpr unsigned IDX = (1u << KeyBits<NB>::idx_bits) - 1u;
     // key-space error model: float32 rounding + truncation of idx_bits mantissa bits is below
@@ -415,6 +424,68 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         int a = 0, b = n;
         ExpSet<NB> rejected;
         bool slow = false;
+        if constexpr (MAD) {
+            double (*sw)[32] = sm.sw[wib];
+            // exact values in key order (their d re-read through L1 / L2; four lookups in flight)
+#pragma unroll 4
+            for (int q = 0; q < n; q++) {
+                const int i = (int)(__float_as_uint(sk[q][lane]) & IDX);
+                const double dd = (double)__ldg(sm.data[i] + v);
+                sw[q][lane] = UNIT ? dd : (sm.offset[i] + dd) * sm.scale[i];
+            }
+            // samples sharing a key bucket are in arbitrary order: local insertion by exact value
+            for (int q = 1; q < n; q++) {
+                if (((__float_as_uint(sk[q][lane]) ^ __float_as_uint(sk[q - 1][lane])) & ~IDX) == 0u) {
+                    for (int r = q; r > 0 && sw[r - 1][lane] > sw[r][lane]; r--) {
+                        const double tw = sw[r][lane]; sw[r][lane] = sw[r - 1][lane]; sw[r - 1][lane] = tw;
+                        const float tk = sk[r][lane]; sk[r][lane] = sk[r - 1][lane]; sk[r - 1][lane] = tk;
+                    }
+                }
+            }
+            if (n >= 2) {
+                int it = A.nmax;
+                for (bool first = true;; first = false) {
+                    const int m = b - a;
+                    if (!first) {                                  // tools.c:61-65 on the compacted, ascending list
+                        double acc = 0.0;
+#pragma unroll 4
+                        for (int q = a; q < b; q++) acc += sw[q][lane];
+                        mean = acc / (double)m;
+                    }
+                    const int ih = a + (m >> 1);
+                    const double med = (m & 1) ? sw[ih][lane] : (sw[ih][lane] + sw[ih - 1][lane]) / 2;   // tools.c:45-48
+                    // middle of |w - med| by merging the two sorted runs outward from the median
+                    int il = (m & 1) ? ih : ih - 1, ir = il + 1;
+                    double cur = 0.0, prev = 0.0;
+                    for (int k = 0; k <= (m >> 1); k++) {
+                        const double dl = il >= a ? fabs(sw[il][lane] - med) : CUDART_INF;
+                        const double dr = ir < b ? fabs(sw[ir][lane] - med) : CUDART_INF;
+                        prev = cur;
+                        if (dl <= dr) { cur = dl; il--; } else { cur = dr; ir++; }
+                    }
+                    const double madv = (m & 1) ? cur : (cur + prev) / 2;
+                    sigma = madv * 1.4826;                         // tools.c:74
+                    const double clo = med - (A.nclip_low * sigma);
+                    const double cup = med + (A.nclip_up * sigma);
+                    // strict window on the ascending exact column: first index with w > clo, first with w >= cup
+                    int lo = a, hi = b;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sw[mid][lane] > clo) hi = mid; else lo = mid + 1; }
+                    const int na = lo;
+                    lo = na; hi = b;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (sw[mid][lane] < cup) lo = mid + 1; else hi = mid; }
+                    const int nb2 = lo;
+                    // NaN bounds (non-finite input): every comparison is false, nothing is inside
+                    const int ni = (clo == clo && cup == cup) ? nb2 - na : 0;
+                    if (ni < nstop || ni == m) break;              // tools.c:140-143
+                    if (it <= 0) break;                            // tools.c:144
+                    it--;
+                    a = na;
+                    b = nb2;
+                }
+                for (int q = 0; q < n; q++)
+                    if (q < a || q >= b) rejected.set_dyn((int)(__float_as_uint(sk[q][lane]) & IDX));
+            }
+        } else
         if (n >= 2 && !(flags & 4)) {
             const double S2_0 = S2;
             int it = A.nmax;

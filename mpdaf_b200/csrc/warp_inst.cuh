@@ -29,10 +29,11 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
     TileArgs<NB> s;
     fill_tile_args(s, j);
     const bool full = (j.nfiles == NB);   // every slot in use: the per-row predicates compile away
-    std::snprintf(ctx.name, ctx.name_len, "sigclip_warp<%d,%s%s>", NB, unit ? "unit" : "scaled", full ? "" : ",partial");
+    const bool mad = j.a.mad != 0;
+    std::snprintf(ctx.name, ctx.name_len, "sigclip_warp<%d,%s%s%s>", NB, unit ? "unit" : "scaled", full ? "" : ",partial",
+                  mad ? ",mad" : "");
     static const int flags = std::getenv("MPDAF_B200_WARP_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : (NB >= 24 ? 1 : 0);
-    auto launch = [&](auto kernel) -> int {
-        const int smem = (int)sizeof(BlockSmem<NB>);
+    auto launch = [&](auto kernel, int smem) -> int {
         MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
         MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWT, smem));
@@ -45,8 +46,18 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
         ctx.launches++;
         return MPDAF_B200_OK;
     };
-    if (unit) return full ? launch(sigclip_warp_kernel<NB, true, true>) : launch(sigclip_warp_kernel<NB, true, false>);
-    return full ? launch(sigclip_warp_kernel<NB, false, true>) : launch(sigclip_warp_kernel<NB, false, false>);
+    if (mad) {   // MAD: one variant per scale mode (row predicates kept: FULL = false)
+        constexpr int smem_mad = (int)sizeof(BlockSmem<NB, true>);
+        if constexpr (smem_mad <= 227 * 1024) {
+            if (unit) return launch(sigclip_warp_kernel<NB, true, false, true>, smem_mad);
+            return launch(sigclip_warp_kernel<NB, false, false, true>, smem_mad);
+        } else {
+            return fail(MPDAF_B200_ERR_ARG, "stack too deep for the MAD warp kernel");
+        }
+    }
+    constexpr int smem = (int)sizeof(BlockSmem<NB>);
+    if (unit) return full ? launch(sigclip_warp_kernel<NB, true, true>, smem) : launch(sigclip_warp_kernel<NB, true, false>, smem);
+    return full ? launch(sigclip_warp_kernel<NB, false, true>, smem) : launch(sigclip_warp_kernel<NB, false, false>, smem);
 }
 
 template <int NB>

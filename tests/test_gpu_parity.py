@@ -96,10 +96,10 @@ def test_mad_and_deep_stacks(n, vartype):
         want = oracle.combine_port(data, var, mad=mad, **kw)
         got = cuda().combine_cuda(data, var, mad=mad, **kw)
         assert_same_result(got, want)
-        if mad or n > 128:
+        if n > 128:
             assert "generic" in cuda().kernel_name()
         else:
-            assert "warp" in cuda().kernel_name()
+            assert "warp" in cuda().kernel_name() and ("mad" in cuda().kernel_name()) == mad
     if n > 64:
         assert_same_result(cuda().median_cuda(data), oracle.median_port(data), median=True)
 
@@ -252,17 +252,35 @@ def test_ill_conditioned_and_extreme_values():
                        oracle.combine_port(data, var, nclip=2.0, vartype="stat_one"), exact_data=True)
 
 
+def test_mad_is_bit_exact():
+    """The MAD variant runs the reference algorithm on exact sorted values: everything identical."""
+    rng = np.random.default_rng(77)
+    c = cuda()
+    for n, ties in ((7, False), (16, True), (48, False), (64, True), (100, False)):
+        data, var = random_stack(rng, n, (3, 9, 11), nan_frac=0.15, outlier_frac=0.08, ties=ties)
+        for kw in (dict(), dict(scales=np.linspace(0.7, 1.4, n), offsets=np.linspace(-1, 1, n))):
+            for vartype in ("propagate", "stat_one"):
+                for nclip in (2.0, (1.0, 3.0)):
+                    want = oracle.combine_port(data, var, mad=True, nclip=nclip, vartype=vartype, nmax=3, **kw)
+                    got = c.combine_cuda(data, var, mad=True, nclip=nclip, vartype=vartype, nmax=3, **kw)
+                    assert "mad" in c.kernel_name()
+                    assert_same_result(got, want, exact_data=True)
+                    if vartype == "stat_one":
+                        np.testing.assert_array_equal(got["var"], want["var"])
+
+
 def test_random_fuzz_against_oracle():
     """Many small random configurations (depth, NaN rate, outliers, parameters, scales)."""
     rng = np.random.default_rng(2025)
     c = cuda()
-    for trial in range(40):
+    for trial in range(60):
         n = int(rng.integers(2, 129))
         shape = (2, int(rng.integers(3, 9)), int(rng.integers(3, 40)))
         data, var = random_stack(rng, n, shape, nan_frac=float(rng.uniform(0, 0.4)),
                                  outlier_frac=float(rng.uniform(0, 0.15)), ties=bool(trial % 5 == 0))
         kw = dict(nmax=int(rng.integers(0, 5)), nclip=(float(rng.uniform(0.8, 5)), float(rng.uniform(0.8, 5))),
-                  nstop=int(rng.integers(1, 5)), vartype=["propagate", "stat_mean", "stat_one"][trial % 3])
+                  nstop=int(rng.integers(1, 5)), vartype=["propagate", "stat_mean", "stat_one"][trial % 3],
+                  mad=bool(trial % 4 == 3))
         if trial % 2:
             kw.update(scales=rng.uniform(0.5, 2.0, n), offsets=rng.uniform(-2, 2, n))
         assert_same_result(c.combine_cuda(data, var, **kw), oracle.combine_port(data, var, **kw))
