@@ -35,6 +35,9 @@
 #ifndef MB_WARP_THREADS
 #define MB_WARP_THREADS 128   // threads per block of the warp-tiled sigma-clip kernel
 #endif
+#ifndef MB_SORT_FMA_EVERY
+#define MB_SORT_FMA_EVERY 0   // every k-th compare-exchange computes its max with 2 IMAD (FMA pipe) instead of IADD3
+#endif
 #ifndef MB_LATE_STAT
 #define MB_LATE_STAT 1   // 1: load the STAT rows after the clip loop (fewer registers, more blocks per SM; +7 %)
 #endif
@@ -310,6 +313,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     const int nfiles = FULL ? NB : A.nfiles;
     const int nstop = A.nstop < 1 ? 1 : A.nstop;
     const bool want_var = (A.typ_var == 0);
+    const unsigned one = (unsigned)(A.nmax > -1000000);    // opaque 1 / -1 for the IMAD compare-exchange form
+    const unsigned minus_one = 0u - one;
 
     for (int i = tid; i < NB; i += kWT) {
         sm.scale[i] = S.scale[i];
@@ -405,7 +410,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         const int n = NB - inval.count();
 
         if (!(flags & 4)) {   // flags & 4: timing experiment only (skips the sort and the clip loop; wrong results)
-        sort_keys_mixed<NB, 0>(key, 0u, 0u);
+        sort_keys_mixed<NB, MB_SORT_FMA_EVERY>(key, one, minus_one);
 #pragma unroll
         for (int q = 0; q < NB; q++) sk[q][lane] = key[q];
         }
