@@ -420,7 +420,8 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
                     }
                 }
             };
-            const int nthreads = (int)std::min<long long>(planes, std::max(1LL, env_ll("MPDAF_B200_IO_THREADS", 8)));
+            const long long hw = std::max(1u, std::thread::hardware_concurrency());
+            const int nthreads = (int)std::min<long long>(planes, std::max(1LL, env_ll("MPDAF_B200_IO_THREADS", std::min(32LL, hw))));
             std::vector<std::thread> pool;
             for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
             for (auto& t : pool) t.join();
