@@ -284,3 +284,64 @@ def test_random_fuzz_against_oracle():
         if trial % 2:
             kw.update(scales=rng.uniform(0.5, 2.0, n), offsets=rng.uniform(-2, 2, n))
         assert_same_result(c.combine_cuda(data, var, **kw), oracle.combine_port(data, var, **kw))
+
+
+# ---- size-independent properties at MUSE plane size (too large for the oracle) --------------------
+
+def _device_run(stack, n, nvox, scales=None, offsets=None, nclip=5.0, vartype=0, median=False):
+    import torch
+    from mpdaf_b200.ctools import DEVICE, check, ctools
+    from mpdaf_b200.cubelist import _ptr_table
+    dev = torch.device("cuda", 0)
+    out = torch.empty(nvox, dtype=torch.float64, device=dev)
+    outvar = torch.empty(nvox, dtype=torch.float64, device=dev)
+    expmap = torch.empty(nvox, dtype=torch.int32, device=dev)
+    kd, dptr = _ptr_table(stack.data_ptrs)
+    kv, vptr = _ptr_table(stack.var_ptrs)
+    valid, select = np.zeros(n, dtype=np.intc), np.zeros(n, dtype=np.intc)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    if median:
+        rc = ctools.mpdaf_b200_median_arrays(n, dptr, 4, nvox, DEVICE, 0, out.data_ptr(), expmap.data_ptr(), valid, stream)
+    else:
+        sp = None if scales is None else scales.ctypes.data
+        op = None if offsets is None else offsets.ctypes.data
+        rc = ctools.mpdaf_b200_sigma_clipping_arrays(n, dptr, vptr, 4, nvox, DEVICE, 0, out.data_ptr(), outvar.data_ptr(),
+                                                     expmap.data_ptr(), sp, op, select, valid, 2, nclip, nclip, 2, vartype, 0, stream)
+    check(rc, "device run")
+    return out, outvar, expmap, valid, select
+
+
+def test_properties_at_muse_plane_size():
+    """48 exposures x 64 MUSE planes (6.9 Mvoxel): checksums, exact power-of-two scaling,
+    permutation of the exposure order."""
+    import torch
+    from mpdaf_b200 import synth
+    from mpdaf_b200.cubelist import DeviceStack
+    n, shape = 48, (64, 326, 331)
+    nvox = int(np.prod(shape))
+    stack, tdata, tvar = synth.device_stack(n, shape, seed=3)
+    scales, offsets = synth.default_scales(n), synth.default_offsets(n)
+    out, outvar, expmap, valid, select = _device_run(stack, n, nvox, scales, offsets)
+    # checksums: every kept sample is counted once in expmap and once in selected_pix
+    assert int(expmap.sum(dtype=torch.int64)) == int(select.astype(np.int64).sum())
+    for i in (0, 17, 47):
+        assert int(valid[i]) == nvox - int(torch.isnan(tdata[i]).sum())
+    assert int((expmap == 0).sum()) == int(torch.isnan(out).sum()) == int(torch.isnan(outvar).sum())
+    assert 0 < int(valid.astype(np.int64).sum() - select.astype(np.int64).sum()) < 0.02 * n * nvox
+    # scaling every exposure by 4 (exact in binary floating point): data x4, var x16, same decisions
+    out4, outvar4, expmap4, valid4, select4 = _device_run(stack, n, nvox, scales * 4.0, offsets)
+    assert torch.equal(expmap4, expmap) and np.array_equal(select4, select)
+    assert torch.equal(torch.nan_to_num(out4), torch.nan_to_num(out * 4.0))
+    assert torch.equal(torch.nan_to_num(outvar4), torch.nan_to_num(outvar * 16.0))
+    # exposure order reversed: same kept sets (counters permuted), means equal to rounding
+    rev = DeviceStack(stack.data_ptrs[::-1], stack.var_ptrs[::-1], shape, 4, 0, keepalive=stack.keepalive)
+    outr, outvarr, expmapr, validr, selectr = _device_run(rev, n, nvox, scales[::-1].copy(), offsets[::-1].copy())
+    assert torch.equal(expmapr, expmap)
+    assert np.array_equal(validr[::-1], valid) and np.array_equal(selectr[::-1], select)
+    good = ~torch.isnan(out)
+    assert float(((outr[good] - out[good]).abs() / out[good].abs()).max()) < 1e-12
+    # median: independent of the exposure order, bit for bit
+    m1 = _device_run(stack, n, nvox, median=True)
+    m2 = _device_run(rev, n, nvox, median=True)
+    assert torch.equal(torch.nan_to_num(m1[0]), torch.nan_to_num(m2[0])) and torch.equal(m1[2], m2[2])
+    assert np.array_equal(m1[3], m2[3][::-1])
