@@ -178,11 +178,11 @@ int launch_tile(const Job& j, bool unit, int device, cudaStream_t stream)
     return launch(sigclip_tile_kernel<NB, false>);
 }
 
-template <int MAXN, typename ElemT>
-int launch_generic(const Job& j, int device, cudaStream_t stream)
+// Uploads the stack description for kernels that read it from device memory.  Ordered on
+// `stream`; no pinned bounce buffer is needed because cudaMemcpyAsync from pageable memory
+// returns after staging the source.
+int upload_table(const Job& j, cudaStream_t stream)
 {
-    // the table upload is ordered on `stream`; a pinned bounce buffer is not needed
-    // because cudaMemcpyAsync from pageable memory returns after staging the source
     static StackTable host;  // guarded by g_call_mutex
     std::memset(&host, 0, sizeof host);
     for (int i = 0; i < j.nfiles; i++) {
@@ -193,6 +193,16 @@ int launch_generic(const Job& j, int device, cudaStream_t stream)
         host.scale2[i] = host.scale[i] * host.scale[i];
     }
     MB_CUDA(cudaMemcpyAsync(j.table_dev, &host, sizeof host, cudaMemcpyHostToDevice, stream));
+    return MPDAF_B200_OK;
+}
+
+template <int MAXN, typename ElemT>
+int launch_generic(const Job& j, int device, cudaStream_t stream)
+{
+    {
+        const int rc = upload_table(j, stream);
+        if (rc != MPDAF_B200_OK) return rc;
+    }
     char name[64];
     std::snprintf(name, sizeof name, "%s_generic<%d,f%d>", j.median ? "median" : "sigclip", MAXN,
                   (int)sizeof(ElemT) * 8);
@@ -239,6 +249,18 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         ctx.name = name;
         ctx.name_len = sizeof name;
         int rc = MPDAF_B200_ERR_ARG;
+        const bool no_two_run = std::getenv("MPDAF_B200_NO_TWO_RUN") != nullptr;
+        const bool force_two_run = std::getenv("MPDAF_B200_TWO_RUN") != nullptr;   // read per call (tests toggle it)
+        // two sorted runs (sigclip_warp2.cuh): measured faster than the single 128-key network only when
+        // scales/offsets are in play (that network spills at 255 registers); MPDAF_B200_TWO_RUN=1 forces it
+        // for every stack deeper than 64
+        if (!j.median && !j.a.mad && nb > 64 && !no_two_run && (force_two_run || (nb == 128 && !unit))) {
+            rc = upload_table(j, stream);
+            if (rc == MPDAF_B200_OK) rc = nb == 96 ? mb_launch_warp2_48(j, unit, ctx) : mb_launch_warp2_64(j, unit, ctx);
+            g_last_kernel = name;
+            g_last_launches += ctx.launches;
+            return rc;
+        }
         switch (nb) {
 #define MB_CASE(NB) case NB: rc = j.median ? mb_launch_median_warp_##NB(j, ctx) : mb_launch_warp_##NB(j, unit, ctx); break;
             MB_FOR_EACH_DEPTH(MB_CASE)

@@ -345,3 +345,17 @@ def test_properties_at_muse_plane_size():
     m2 = _device_run(rev, n, nvox, median=True)
     assert torch.equal(torch.nan_to_num(m1[0]), torch.nan_to_num(m2[0])) and torch.equal(m1[2], m2[2])
     assert np.array_equal(m1[3], m2[3][::-1])
+
+
+def test_two_run_kernel_for_deep_stacks(monkeypatch):
+    """sigclip_warp2 (two sorted runs, k-th of two sorted columns) on every deep-stack shape."""
+    monkeypatch.setenv("MPDAF_B200_TWO_RUN", "1")
+    rng = np.random.default_rng(4242)
+    c = cuda()
+    for n in (65, 80, 96, 97, 112, 128):
+        data, var = random_stack(rng, n, (2, 7, 19), nan_frac=0.2, outlier_frac=0.08, ties=(n % 2 == 0))
+        for kw in (dict(), dict(scales=np.linspace(0.6, 1.7, n), offsets=np.linspace(-2, 2, n))):
+            for vartype, nclip, nmax in (("propagate", 2.0, 2), ("stat_mean", (1.5, 3.0), 4), ("stat_one", 5.0, 1)):
+                want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, nmax=nmax, **kw)
+                got = c.combine_cuda(data, var, vartype=vartype, nclip=nclip, nmax=nmax, **kw)
+                assert_same_result(got, want)
