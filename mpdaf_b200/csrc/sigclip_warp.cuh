@@ -364,7 +364,6 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         const long long tile = tile0 + wib;
         const long long v = (tile << 5) + lane;
         const bool act = tile < ntiles && v < A.nvox;
-        if (tile + wstride < ntiles) prefetch_rows(false, tile + wstride);
         if (want_var && (flags & 8)) prefetch_rows(true, tile);   // flags & 8: STAT prefetch at tile start (3 % slower)
 
         // ---- gather: one coalesced load per exposure ------------------------------------------
@@ -377,6 +376,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
         }
         asm volatile("" ::: "memory");
+        // next tile's DATA rows into L1: issued behind the gather so that its address loads overlap the gather latency
+        if (tile + wstride < ntiles) prefetch_rows(false, tile + wstride);
 
         // ---- pass 1: exposure order.  w, exact sum, shifted moments, keys ----------------------
         ExpSet<NB> inval;
@@ -580,21 +581,35 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         const ExpSet<NB> dropped = inval | rejected;
         double vsum = 0.0;
 #if MB_LATE_STAT
-        // STAT rows loaded only now (they were prefetched into L1 at the start of the tile): fewer live
-        // registers across the clip loop, one more resident block per SM
+        // STAT rows loaded only now (prefetched into L1 after the sort): fewer live registers across the
+        // clip loop, more resident blocks per SM.  Two half-batches: the second is in flight while the
+        // first is consumed.
         float sv[NB];
         if (want_var) {
             const long long vs = act ? v : A.nvox - 1;
+            constexpr int HB = NB / 2;
 #pragma unroll
-            for (int i = 0; i < NB; i++)
+            for (int i = 0; i < HB; i++)
                 asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
+#pragma unroll
+            for (int i = HB; i < NB; i++)
+                asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < HB; i++)
+                if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int i = HB; i < NB; i++)
+                if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];
         }
-#endif
+#else
         if (want_var) {
 #pragma unroll
             for (int i = 0; i < NB; i++)
                 if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
         }
+#endif
 
         // ---- per-exposure counters: transpose the lanes' masks, one POPC per lane --------------
         if constexpr (NB > 32 && NB <= 48) {
