@@ -294,6 +294,22 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
             case 64: return launch_reg<64>(j, unit, device, stream);
         }
     }
+    // 129..512 float32 exposures, plain sigma clip: R sorted runs of 64 (sigclip_runs.cuh)
+    if (j.nfiles > 128 && j.nfiles <= kGenericMax && j.elem == MPDAF_B200_F32 && !j.median && !j.a.mad &&
+        which == "warp" && std::getenv("MPDAF_B200_NO_RUNS") == nullptr) {
+        char name[64] = "";
+        LaunchCtx ctx;
+        ctx.sm_count = g_dev[device].sm_count;
+        ctx.slow = g_dev[device].slow;
+        ctx.stream = stream;
+        ctx.name = name;
+        ctx.name_len = sizeof name;
+        int rc = upload_table(j, stream);
+        if (rc == MPDAF_B200_OK) rc = mb_launch_runs(j, unit, ctx);
+        g_last_kernel = name;
+        g_last_launches += ctx.launches;
+        return rc;
+    }
     if (j.nfiles <= 128) {
         if (j.elem == MPDAF_B200_F32) return launch_generic<128, float>(j, device, stream);
         return launch_generic<128, double>(j, device, stream);

@@ -54,3 +54,5 @@ MB_FOR_EACH_DEPTH(MB_DECLARE_DEPTH)
 // two-run kernels for deep stacks (sigclip_warp2.cuh); the stack table must already be on the device
 int mb_launch_warp2_48(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);
 int mb_launch_warp2_64(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);
+// multi-run kernel for 129..512 exposures (sigclip_runs.cuh); same precondition
+int mb_launch_runs(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);

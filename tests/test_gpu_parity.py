@@ -97,7 +97,7 @@ def test_mad_and_deep_stacks(n, vartype):
         got = cuda().combine_cuda(data, var, mad=mad, **kw)
         assert_same_result(got, want)
         if n > 128:
-            assert "generic" in cuda().kernel_name()
+            assert ("generic" if mad else "sigclip_runs") in cuda().kernel_name()
         else:
             assert "warp" in cuda().kernel_name() and ("mad" in cuda().kernel_name()) == mad
     if n > 64:
@@ -359,3 +359,25 @@ def test_two_run_kernel_for_deep_stacks(monkeypatch):
                 want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, nmax=nmax, **kw)
                 got = c.combine_cuda(data, var, vartype=vartype, nclip=nclip, nmax=nmax, **kw)
                 assert_same_result(got, want)
+
+
+@pytest.mark.parametrize("n", [129, 150, 192, 256, 257, 300, 448, 500])
+def test_multi_run_kernel_for_very_deep_stacks(n):
+    """sigclip_runs (R sorted runs of 64, k-th of R sorted columns by bisection) for 129..512 exposures."""
+    rng = np.random.default_rng(n)
+    c = cuda()
+    data, var = random_stack(rng, n, (2, 5, 23), nan_frac=0.25, outlier_frac=0.08, ties=(n % 2 == 0))
+    for i, d in enumerate(data):
+        d[0, 0, :3] = np.nan                         # empty voxels
+        if i > 0:
+            d[0, 1, 0] = np.nan                      # a single valid sample
+        d[0, 2, 0] = 7.25                            # zero spread
+        if i < n // 2:
+            d[1, 0, 0] = np.nan                      # a whole run (and more) invalid
+    data[0][0, 1, 0] = 3.5
+    for kw in (dict(), dict(scales=np.linspace(0.6, 1.7, n), offsets=np.linspace(-2, 2, n))):
+        for vartype, nclip, nmax, nstop in (("propagate", 2.0, 2, 2), ("stat_mean", (1.5, 3.0), 6, 2), ("stat_one", 1.0, 30, n // 2)):
+            want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, nmax=nmax, nstop=nstop, **kw)
+            got = c.combine_cuda(data, var, vartype=vartype, nclip=nclip, nmax=nmax, nstop=nstop, **kw)
+            assert "sigclip_runs" in c.kernel_name()
+            assert_same_result(got, want)
