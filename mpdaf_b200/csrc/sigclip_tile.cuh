@@ -43,6 +43,7 @@ struct TileArgs {
     double scale[NB];
     double offset[NB];
     double scale2[NB];
+    unsigned dstride, vstride;   // elements between consecutive DATA / STAT rows when equally spaced, else 0
 };
 
 template <int NB>

@@ -295,7 +295,10 @@ template <int NB> struct WarpBlocks { static constexpr int value = (NB <= 48 ? M
 // of absolute deviations left and right of the median (outward merge), exact strict window counts
 // by binary search on the float64 column, ascending-order sums for the later means.  No error
 // bounds are involved in this mode: every output is the reference's, bit for bit.
-template <int NB, bool UNIT, bool FULL, bool MAD = false>
+// STRIDED: the rows of the stack are equally spaced in memory (one [N][V] allocation, the layout of the
+// slab slots and of any stacked tensor): row i+1 = row i + S.dstride elements, so an address costs one
+// IMAD.WIDE on the FMA pipe instead of a constant-bank load plus a 64-bit add on the ALU pipe.
+template <int NB, bool UNIT, bool FULL, bool MAD = false, bool STRIDED = false>
 __global__ void __launch_bounds__(kWT, WarpBlocks<NB>::value)
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
                     const int flags, unsigned long long* slow_total)
@@ -354,6 +357,9 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             }
         }
     };
+    // (prefetch.global.L1 only reaches L2 on this part -- tools/microbench/l1prefetch.cu: a later load still
+    // takes the ~480-cycle L2 latency.  Real L1 fills, cp.async.ca of one word per sector into a dummy
+    // shared-memory word, make the later load a 33-cycle L1 hit but measured 10-18 % slower here.)
     if (tile0 + wib < ntiles) prefetch_rows(false, tile0 + wib);
 
     // The trip count is uniform per block so that the optional per-tile barrier is legal; a warp
@@ -368,12 +374,18 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 
         // ---- gather: one coalesced load per exposure ------------------------------------------
         float key[NB];
+        const float* rp = S.data[0] + v;
 #pragma unroll
         for (int i = 0; i < NB; i++) {
             // predicated loads: ptxas keeps them batched at the top of the tile (unconditional
             // ones get sunk next to their first use and their latency serialises)
             key[i] = CUDART_NAN_F;
-            if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
+            if constexpr (STRIDED) {
+                if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(rp));
+                asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(rp) : "r"(S.dstride));
+            } else {
+                if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
+            }
         }
         asm volatile("" ::: "memory");
         // next tile's DATA rows into L1: issued behind the gather so that its address loads overlap the gather latency
@@ -588,12 +600,25 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         if (want_var) {
             const long long vs = act ? v : A.nvox - 1;
             constexpr int HB = NB / 2;
+            const float* vp = S.var[0] + vs;
 #pragma unroll
-            for (int i = 0; i < HB; i++)
-                asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
+            for (int i = 0; i < HB; i++) {
+                if constexpr (STRIDED) {
+                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(vp));
+                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(vp) : "r"(S.vstride));
+                } else {
+                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
+                }
+            }
 #pragma unroll
-            for (int i = HB; i < NB; i++)
-                asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
+            for (int i = HB; i < NB; i++) {
+                if constexpr (STRIDED) {
+                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(vp));
+                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(vp) : "r"(S.vstride));
+                } else {
+                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
+                }
+            }
             asm volatile("" ::: "memory");
 #pragma unroll
             for (int i = 0; i < HB; i++)

@@ -20,6 +20,17 @@ void fill_tile_args(TileArgs<NB>& s, const Job& j)
         s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
         s.scale2[i] = s.scale[i] * s.scale[i];
     }
+    // equally spaced rows (one [N][V] allocation): the STRIDED kernels step from row to row
+    auto stride_of = [&](const void* const* rows) -> unsigned {
+        if (rows == nullptr || j.nfiles != NB || NB < 2) return 0u;
+        const long long step = static_cast<const char*>(rows[1]) - static_cast<const char*>(rows[0]);
+        if (step <= 0 || (step & 3) != 0 || (step >> 2) > 0xFFFFFFFFLL) return 0u;
+        for (int i = 2; i < NB; i++)
+            if (static_cast<const char*>(rows[i]) - static_cast<const char*>(rows[i - 1]) != step) return 0u;
+        return (unsigned)(step >> 2);
+    };
+    s.dstride = stride_of(j.data);
+    s.vstride = stride_of(j.var);
 }
 
 // Warp-tiled sigma clip (sigclip_warp.cuh): the main kernel for float32 stacks up to 128 deep.
@@ -56,6 +67,13 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
         }
     }
     constexpr int smem = (int)sizeof(BlockSmem<NB>);
+    static const bool no_strided = std::getenv("MPDAF_B200_NO_STRIDED") != nullptr;
+    const bool strided = full && !no_strided && s.dstride != 0 && (j.a.typ_var != 0 || s.vstride != 0);
+    if (strided) {
+        std::snprintf(ctx.name, ctx.name_len, "sigclip_warp<%d,%s,strided>", NB, unit ? "unit" : "scaled");
+        if (unit) return launch(sigclip_warp_kernel<NB, true, true, false, true>, smem);
+        return launch(sigclip_warp_kernel<NB, false, true, false, true>, smem);
+    }
     if (unit) return full ? launch(sigclip_warp_kernel<NB, true, true>, smem) : launch(sigclip_warp_kernel<NB, true, false>, smem);
     return full ? launch(sigclip_warp_kernel<NB, false, true>, smem) : launch(sigclip_warp_kernel<NB, false, false>, smem);
 }

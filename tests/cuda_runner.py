@@ -50,8 +50,25 @@ def combine_cuda(data, var=None, scales=None, offsets=None, nmax=2, nclip=5.0, n
         import torch
         dev = torch.device("cuda", device)
         tdt = torch.float32 if dt == np.float32 else torch.float64
-        td = [torch.from_numpy(a.reshape(-1)).to(dev) for a in data]
-        tv = None if var is None else [torch.from_numpy(a.reshape(-1)).to(dev) for a in var]
+        if location == "device_stacked":      # one [N][V] allocation: equally spaced rows
+            sd = torch.from_numpy(np.stack([a.reshape(-1) for a in data])).to(dev)
+            td = list(sd)
+            tv = None if var is None else list(torch.from_numpy(np.stack([a.reshape(-1) for a in var])).to(dev))
+        elif location == "device_scattered":  # rows at irregular distances inside one pool
+            gaps = [0] + [32 * (1 + (7 * i) % 5) for i in range(n)]
+            starts = [int(sum(gaps[: i + 1]) + i * nvox) for i in range(n)]
+            pool_d = torch.full((starts[-1] + nvox + 32,), float("nan"), dtype=tdt, device=dev)
+            pool_v = torch.full((starts[-1] + nvox + 32,), float("nan"), dtype=tdt, device=dev)
+            td, tv = [], (None if var is None else [])
+            for i in range(n):
+                td.append(pool_d[starts[i]: starts[i] + nvox])
+                td[-1].copy_(torch.from_numpy(data[i].reshape(-1)))
+                if var is not None:
+                    tv.append(pool_v[starts[i]: starts[i] + nvox])
+                    tv[-1].copy_(torch.from_numpy(var[i].reshape(-1)))
+        else:
+            td = [torch.from_numpy(a.reshape(-1)).to(dev) for a in data]
+            tv = None if var is None else [torch.from_numpy(a.reshape(-1)).to(dev) for a in var]
         tout = torch.empty(max(nvox, 1), dtype=torch.float64, device=dev)
         tvar = torch.empty(max(nvox, 1), dtype=torch.float64, device=dev)
         texp = torch.empty(max(nvox, 1), dtype=torch.int32, device=dev)

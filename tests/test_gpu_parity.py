@@ -381,3 +381,22 @@ def test_multi_run_kernel_for_very_deep_stacks(n):
             got = c.combine_cuda(data, var, vartype=vartype, nclip=nclip, nmax=nmax, nstop=nstop, **kw)
             assert "sigclip_runs" in c.kernel_name()
             assert_same_result(got, want)
+
+
+@pytest.mark.parametrize("n", [4, 16, 24, 48, 64, 96, 128])
+def test_equally_spaced_and_scattered_rows_agree(n):
+    """The STRIDED kernels (rows of one [N][V] allocation) and the pointer-table kernels are the same arithmetic."""
+    rng = np.random.default_rng(900 + n)
+    c = cuda()
+    data, var = random_stack(rng, n, (3, 11, 37), nan_frac=0.15, outlier_frac=0.06)
+    for kw in (dict(), dict(scales=np.linspace(0.8, 1.3, n), offsets=np.linspace(-1, 1, n))):
+        for vartype in ("propagate", "stat_mean"):
+            want = oracle.combine_port(data, var, vartype=vartype, nclip=2.5, **kw)
+            a = c.combine_cuda(data, var, vartype=vartype, nclip=2.5, location="device_stacked", **kw)
+            assert "strided" in c.kernel_name() or "sigclip_warp<" not in c.kernel_name()
+            b = c.combine_cuda(data, var, vartype=vartype, nclip=2.5, location="device_scattered", **kw)
+            assert "strided" not in c.kernel_name()
+            assert_same_result(a, want)
+            assert_same_result(b, want)
+            for key in ("data", "var", "expmap", "select_pix", "valid_pix"):
+                np.testing.assert_array_equal(a[key], b[key])
