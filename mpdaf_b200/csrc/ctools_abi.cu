@@ -75,6 +75,8 @@ int device_ready(int device)
     if (prop.major != 10)
         return fail(MPDAF_B200_ERR_CUDA, "device is not sm_100 (Blackwell B200); kernels are built for sm_100a only");
     d.sm_count = prop.multiProcessorCount;
+    // tuning hook: MPDAF_B200_L2_FETCH = 32 | 64 | 128 sets the L2 fetch granularity hint (default: the driver's, 64)
+    if (const char* g = std::getenv("MPDAF_B200_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
     MB_CUDA(cudaMalloc(&d.counters, 2 * kGenericMax * sizeof(unsigned long long)));
     MB_CUDA(cudaMalloc(&d.table, sizeof(StackTable)));
     MB_CUDA(cudaMalloc(&d.slow, sizeof(unsigned long long)));

@@ -44,6 +44,12 @@ struct TileArgs {
     double offset[NB];
     double scale2[NB];
     unsigned dstride, vstride;   // elements between consecutive DATA / STAT rows when equally spaced, else 0
+    // float32 images of the per-exposure constants (warp kernel): key = d * kscale + koffset, STAT * scale2f
+    double2 os[NB];              // (offset, scale) side by side: one 128-bit uniform load per exposure
+    float kscale[NB];
+    float koffset[NB];
+    float scale2f[NB];
+    double koff;                 // bound on |key-before-truncation - float32(w)| from the offsets, part of the margins
 };
 
 template <int NB>

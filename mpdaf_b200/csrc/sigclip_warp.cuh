@@ -38,6 +38,34 @@
 #ifndef MB_SORT_FMA_EVERY
 #define MB_SORT_FMA_EVERY 0   // every k-th compare-exchange computes its max with 2 IMAD (FMA pipe) instead of IADD3
 #endif
+#ifndef MB_EXACT_SUM
+#define MB_EXACT_SUM 1   // 1: also carry sum(w) in exposure order, so an unclipped mean is the reference's to the bit
+#endif
+#ifndef MB_KEY_FFMA
+#define MB_KEY_FFMA 0    // 1: key = float32 FMA of the raw sample (FMA pipe + 2 constant loads) instead of float32(w) (XU pipe)
+#endif
+#ifndef MB_PREFETCH_FULL_LINE
+#define MB_PREFETCH_FULL_LINE 1   // prefetch both 64-byte halves of every line
+#endif
+#ifndef MB_TIMING
+#define MB_TIMING 0      // 1 (tuning builds only): per-phase clock64 totals of blocks 0 and 400, printed at the end
+#endif
+#if MB_TIMING
+#define MB_STAMP(k) do { const long long c_ = clock64(); if (lane == 0) sm.tph[wib][k] += (unsigned long long)(c_ - tprev); tprev = c_; } while (0)
+#define MB_TOUCH(x) do { unsigned u_; asm volatile("mov.b32 %0, %1;" : "=r"(u_) : "f"(x)); } while (0)
+#else
+#define MB_STAMP(k) do { } while (0)
+#define MB_TOUCH(x) do { } while (0)
+#endif
+#ifndef MB_ABLATE
+#define MB_ABLATE 0      // 1 (tuning builds only): flags 32 / 64 / 128 replace memory traffic by L1-resident accesses
+#endif
+#ifndef MB_P1_CHAINS
+#define MB_P1_CHAINS 1
+#endif
+#ifndef MB_VAR_F32
+#define MB_VAR_F32 1     // 1: propagated variance accumulated by float32 FMAs in short chains (<= 4e-7 relative for N <= 64)
+#endif
 #ifndef MB_LATE_STAT
 #define MB_LATE_STAT 1   // 1: load the STAT rows after the clip loop (fewer registers, more blocks per SM; +7 %)
 #endif
@@ -106,8 +134,12 @@ struct BlockSmem {
     double scale[NB];
     double offset[NB];
     double rcp[NB + 1];   // 1.0 / m
-    const float* data[NB];   // exposure base pointers (lane-dependent lookups of rejected samples)
+    const float* data[NB];   // exposure base pointers (lane-dependent lookups of rejected samples, prefetch)
+    const float* var[NB];
     double sw[MAD ? kWT / 32 : 1][MAD ? NB : 1][32];   // MAD: exact w in ascending order, one column per lane
+#if MB_TIMING
+    unsigned long long tph[kWT / 32][12];
+#endif
 };
 
 // compare-exchange variants: the max as a + b - min on the ALU (IADD3) or on the FMA pipe (2 IMAD)
@@ -318,14 +350,24 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     const bool want_var = (A.typ_var == 0);
     const unsigned one = (unsigned)(A.nmax > -1000000);    // opaque 1 / -1 for the IMAD compare-exchange form
     const unsigned minus_one = 0u - one;
+    // ~IDX in a register the compiler cannot fold: (key & mask) | index is then ONE three-input LOP3
+    const unsigned keep_mask = ~IDX ^ (unsigned)(A.nmax < -1000000);
 
     for (int i = tid; i < NB; i += kWT) {
-        sm.scale[i] = S.scale[i];
-        sm.offset[i] = S.offset[i];
+        sm.scale[i] = S.os[i].y;
+        sm.offset[i] = S.os[i].x;
         sm.data[i] = S.data[i];
+        sm.var[i] = S.var[i];
     }
     for (int i = tid; i <= NB; i += kWT) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
+#if MB_TIMING
+    if (tid < 48) sm.tph[tid / 12][tid % 12] = 0ull;
+    long long tprev = 0;
+#endif
     __syncthreads();   // the only block-wide barrier of the kernel (unless flags & 1)
+#if MB_TIMING
+    tprev = clock64();
+#endif
 
     float (*sk)[32] = sm.w[wib].k;
     TransposeConsts tc;
@@ -344,16 +386,25 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     // prefetch of a tile's rows: lane l touches rows l, l + 32, ... (one 128-byte line each);
     // into L1 by default (measured 12 % faster than L2 only; flags & 2 selects L2)
     const bool l1 = (flags & 2) == 0;
+    // A prefetch fetches 64 bytes (the default L2 fetch granularity: measured as a 50 % L2 hit rate of the
+    // gather when one address per line was prefetched), so each 128-byte line takes two: slot j = row * 2 + half.
     auto prefetch_rows = [&](bool stat, long long t) {
         const long long v0 = t << 5;
         if (v0 + 31 >= A.nvox) return;
+        constexpr int HALVES = MB_PREFETCH_FULL_LINE ? 2 : 1;
 #pragma unroll
-        for (int r = 0; r < W; r++) {
-            const int i = lane + 32 * r;
+        for (int r = 0; r < (HALVES * NB + 31) / 32; r++) {
+            const int j = lane + 32 * r;
+            const int i = HALVES == 2 ? (j >> 1) : j;
             if (i < nfiles) {
-                const float* row = stat ? S.var[i] : S.data[i];
-                if (l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(row + v0));
-                else asm volatile("prefetch.global.L2 [%0];" ::"l"(row + v0));
+                // lane-dependent row: never index the constant bank with it (a divergent LDC replays once per
+                // distinct address); equally spaced rows are computed, the others come from shared memory
+                const float* row;
+                if constexpr (STRIDED) row = stat ? S.var[0] + (size_t)i * S.vstride : S.data[0] + (size_t)i * S.dstride;
+                else row = stat ? sm.var[i] : sm.data[i];
+                row += v0 + (HALVES == 2 ? (j & 1) * 16 : 0);
+                if (l1) asm volatile("prefetch.global.L1 [%0];" ::"l"(row));
+                else asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
             }
         }
     };
@@ -361,12 +412,14 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     // takes the ~480-cycle L2 latency.  Real L1 fills, cp.async.ca of one word per sector into a dummy
     // shared-memory word, make the later load a 33-cycle L1 hit but measured 10-18 % slower here.)
     if (tile0 + wib < ntiles) prefetch_rows(false, tile0 + wib);
+    if (want_var && (flags & 16) && tile0 + wib < ntiles) prefetch_rows(true, tile0 + wib);
 
     // The trip count is uniform per block so that the optional per-tile barrier is legal; a warp
     // whose last tile lies beyond the range runs it with every lane idle.
     for (; tile0 < ntiles; tile0 += wstride) {
         // flags & 1 (experiment, slower): the four warps of a block start every tile together
         if (flags & 1) __syncthreads();
+        MB_STAMP(0);   // barrier wait
         const long long tile = tile0 + wib;
         const long long v = (tile << 5) + lane;
         const bool act = tile < ntiles && v < A.nvox;
@@ -374,7 +427,13 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 
         // ---- gather: one coalesced load per exposure ------------------------------------------
         float key[NB];
+#if MB_ABLATE   // tuning builds: flags & 32 gathers from an L1-resident window (LSU work without L2 / DRAM)
+        const float* rp = (flags & 32) ? S.data[0] + (v & 1023) : S.data[0] + v;
+        const unsigned gstride = (flags & 32) ? 32u : S.dstride;
+#else
         const float* rp = S.data[0] + v;
+        const unsigned gstride = S.dstride;
+#endif
 #pragma unroll
         for (int i = 0; i < NB; i++) {
             // predicated loads: ptxas keeps them batched at the top of the tile (unconditional
@@ -382,45 +441,75 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             key[i] = CUDART_NAN_F;
             if constexpr (STRIDED) {
                 if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(rp));
-                asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(rp) : "r"(S.dstride));
+                asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(rp) : "r"(gstride));
             } else {
                 if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
             }
         }
         asm volatile("" ::: "memory");
         // next tile's DATA rows into L1: issued behind the gather so that its address loads overlap the gather latency
-        if (tile + wstride < ntiles) prefetch_rows(false, tile + wstride);
+        if (tile + wstride < ntiles && !(MB_ABLATE && (flags & 128))) prefetch_rows(false, tile + wstride);
+        if (want_var && (flags & 16) && tile + wstride < ntiles) prefetch_rows(true, tile + wstride);   // flags & 16: STAT a tile ahead as well
+        MB_STAMP(1);   // gather + prefetch issue
+#if MB_TIMING
+#pragma unroll
+        for (int i = 0; i < NB; i++) MB_TOUCH(key[i]);
+#endif
+        MB_STAMP(2);   // DATA arrival
 
-        // ---- pass 1: exposure order.  w, exact sum, shifted moments, keys ----------------------
+        // ---- pass 1: exposure order.  w, shifted moments, keys ----------------------------------
+        // Straight-line, 11-12 instructions per exposure: one conversion, (offset + d) * scale exactly as
+        // merging.c:426, t = w - p, and one PTX block that does everything depending on "d is not NaN"
+        // under a predicate (moment updates, invalid bit, sentinel select) -- no branch per exposure.
         ExpSet<NB> inval;
-        double sum = 0.0, T1 = 0.0, S2 = 0.0, p = 0.0;
+        // MB_P1_CHAINS independent accumulator chains: the 48-deep dependent chains of float64 adds were the
+        // critical path of this pass (the pipe has a long latency and only six warps share a scheduler)
+        constexpr int NCH = MB_P1_CHAINS;
+        double sum = 0.0, p = 0.0, T1c[NCH], S2c[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; c++) { T1c[c] = 0.0; S2c[c] = 0.0; }
         bool have_p = false;
 #pragma unroll
         for (int i = 0; i < NB; i++) {
             const float d = key[i];
-            const bool ok = (d == d);
+            const unsigned sentinel = (0x7F7FFFFFu & ~IDX) | (unsigned)i;
             double w;
-            if constexpr (UNIT) w = (double)d;
-            else w = (S.offset[i] + (double)d) * S.scale[i];
+            float kf;
+            if constexpr (UNIT) {
+                w = (double)d;
+                kf = d;
+            } else {
+                w = (S.os[i].x + (double)d) * S.os[i].y;
+#if MB_KEY_FFMA
+                kf = __fmaf_rn(d, S.kscale[i], S.koffset[i]);
+#else
+                kf = __double2float_rn(w);
+#endif
+            }
             if (i < 4) {                       // pivot = first valid sample among the first four
+                const bool ok = (d == d);
                 p = (ok && !have_p) ? w : p;
                 have_p = have_p || ok;
             }
-            if (ok) {                          // (a predicated-PTX spelling of this block measured 13 % slower)
-                sum += w;                      // tools.c:13-16, exposure order, no FMA
-                const double t = w - p;
-                T1 += t;
-                S2 = __fma_rn(t, t, S2);
-            } else {
-                inval.set(i);
-            }
-            float kf;
-            if constexpr (UNIT) kf = d;
-            else kf = __double2float_rn(w);
-            const unsigned kb = (__float_as_uint(kf) & ~IDX) | (unsigned)i;
-            key[i] = fminf(__uint_as_float(kb), __uint_as_float((0x7F7FFFFFu & ~IDX) | (unsigned)i));  // NaN -> sentinel
+            const bool ok = (d == d);
+            // invalid sample: t becomes a denormal (high word cleared, at most 2^-1042 in magnitude) with ONE
+            // select; the unconditional moment updates below then add nothing that survives a rounding
+            double t = w - p;
+            t = __hiloint2double(ok ? __double2hiint(t) : 0, __double2loint(t));
+#if MB_EXACT_SUM
+            sum += ok ? w : 0.0;               // tools.c:13-16, exposure order, no FMA
+#endif
+            T1c[i % NCH] += t;
+            S2c[i % NCH] = __fma_rn(t, t, S2c[i % NCH]);
+            if (!ok) inval.set(i);
+            const unsigned kb = (__float_as_uint(kf) & keep_mask) | (unsigned)i;
+            key[i] = __uint_as_float(ok ? kb : sentinel);
         }
+        double T1 = T1c[0], S2 = S2c[0];
+#pragma unroll
+        for (int c = 1; c < NCH; c++) { T1 += T1c[c]; S2 += S2c[c]; }
         const int n = NB - inval.count();
+        MB_STAMP(3);   // pass 1
 
         if (!(flags & 4)) {   // flags & 4: timing experiment only (skips the sort and the clip loop; wrong results)
         sort_keys_mixed<NB, MB_SORT_FMA_EVERY>(key, one, minus_one);
@@ -429,7 +518,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         }
         // the STAT rows are prefetched into L1 only now: close enough to their use (after the clip
         // loop) that they are still there, early enough that the latency is covered
-        if (want_var && !(flags & 8)) prefetch_rows(true, tile);
+        if (want_var && !(flags & (8 | 16)) && !(MB_ABLATE && (flags & 128))) prefetch_rows(true, tile);
+        MB_STAMP(4);   // sort + column store + STAT prefetch
 
 #if !MB_LATE_STAT
         // STAT rows: issued now, into the registers the keys just vacated, consumed after the clip
@@ -445,7 +535,11 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 #endif
 
         // ---- clip iterations on the sorted column --------------------------------------------
+#if MB_EXACT_SUM
         double mean = sum / (double)n;             // n == 0 -> NaN (merging.c:439)
+#else
+        double mean = n > 0 ? p + T1 * sm.rcp[n] : CUDART_NAN;
+#endif
         double sigma = 0.0;
         int a = 0, b = n;
         ExpSet<NB> rejected;
@@ -538,7 +632,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 // total uncertainty of a key against a bound: median from truncated keys,
                 // sigma from reordered sums, key truncation of the sample itself
                 const double spread = (A.nclip_low + A.nclip_up) * sigma;
-                const double T = KEPS * amax + 0x1p-26 * spread + KEPS * (fabs(clo) + fabs(cup)) + 0x1p-120;
+                const double T = KEPS * amax + 0x1p-26 * spread + KEPS * (fabs(clo) + fabs(cup)) + S.koff;
                 if (!(T < 0x1p120)) { slow = true; break; }   // NaN / inf bounds: let the exact path decide
                 // keys certainly at or below the low bound / certainly below the high bound
                 const float f_lo_in = __double2float_ru(clo + T), f_lo_out = __double2float_rd(clo - T);
@@ -561,16 +655,35 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 if (ni < nstop || ni == m) break;                         // tools.c:100-103
                 if (it <= 0) break;                                       // tools.c:104
                 it--;
-                // drop the rejected samples [a,na) and [nb2,b): exact w recomputed from the samples
-                for (int q = a; q < b; q++) {
-                    if (q == na) { q = nb2; if (q >= b) break; }
-                    const int i = (int)(__float_as_uint(sk[q][lane]) & IDX);
-                    const double dd = (double)__ldg(sm.data[i] + v);   // L1 / L2 hit: loaded by this warp just now
-                    const double w = UNIT ? dd : (sm.offset[i] + dd) * sm.scale[i];
-                    const double t = w - p;
-                    T1 -= t;
-                    S2 -= t * t;
-                    rejected.set_dyn(i);
+                // drop the rejected samples [a,na) and [nb2,b): exact w recomputed from the samples, which are
+                // re-read through L1 / L2 (this warp loaded them a moment ago) four at a time, so that a
+                // voxel's lookups share one memory latency instead of queueing up behind each other
+                const int r1 = na - a, r = r1 + (b - nb2);
+                for (int k0 = 0; k0 < r; k0 += 4) {
+                    float dv[4];
+                    int iv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int k = k0 + j;
+                        const int q = k < r ? (k < r1 ? a + k : nb2 + (k - r1)) : a;
+                        iv[j] = (int)(__float_as_uint(sk[q][lane]) & IDX);
+                        const float* src;
+                        if constexpr (STRIDED) src = S.data[0] + (size_t)iv[j] * S.dstride + v;
+                        else src = sm.data[iv[j]] + v;
+                        dv[j] = 0.f;
+                        if (k < r) dv[j] = __ldg(src);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (k0 + j < r) {
+                            const double dd = (double)dv[j];
+                            const double w = UNIT ? dd : (sm.offset[iv[j]] + dd) * sm.scale[iv[j]];
+                            const double t = w - p;
+                            T1 -= t;
+                            S2 -= t * t;
+                            rejected.set_dyn(iv[j]);
+                        }
+                    }
                 }
                 a = na;
                 b = nb2;
@@ -588,6 +701,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             slow_count++;
         }
         __syncwarp();
+        MB_STAMP(5);   // clip loop
 
         // ---- propagated variance over the kept set --------------------------------------------
         const ExpSet<NB> dropped = inval | rejected;
@@ -600,12 +714,18 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         if (want_var) {
             const long long vs = act ? v : A.nvox - 1;
             constexpr int HB = NB / 2;
+#if MB_ABLATE   // flags & 64: STAT from an L1-resident window
+            const float* vp = (flags & 64) ? S.var[0] + (vs & 1023) : S.var[0] + vs;
+            const unsigned sstride = (flags & 64) ? 32u : S.vstride;
+#else
             const float* vp = S.var[0] + vs;
+            const unsigned sstride = S.vstride;
+#endif
 #pragma unroll
             for (int i = 0; i < HB; i++) {
                 if constexpr (STRIDED) {
                     asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(vp));
-                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(vp) : "r"(S.vstride));
+                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(vp) : "r"(sstride));
                 } else {
                     asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
                 }
@@ -614,12 +734,38 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             for (int i = HB; i < NB; i++) {
                 if constexpr (STRIDED) {
                     asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(vp));
-                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(vp) : "r"(S.vstride));
+                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(vp) : "r"(sstride));
                 } else {
                     asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(S.var[i < nfiles ? i : 0] + vs));
                 }
             }
             asm volatile("" ::: "memory");
+            MB_STAMP(6);   // STAT issue
+#if MB_TIMING
+#pragma unroll
+            for (int i = 0; i < NB; i++) MB_TOUCH(sv[i]);
+#endif
+            MB_STAMP(7);   // STAT arrival
+#if MB_VAR_F32
+            if constexpr (!MAD) {
+            // float32 FMAs in NACC interleaved chains (each <= 8 terms for N <= 64), chains summed in
+            // float64: <= (NB / NACC + 2) * 2^-24 relative for non-negative STAT, inside the 1e-6 contract
+            constexpr int NACC = NB <= 8 ? 1 : (NB <= 16 ? 2 : (NB <= 32 ? 4 : (NB <= 64 ? 8 : 16)));
+            float vacc[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; k++) vacc[k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < HB; i++)
+                if (!dropped.test(i)) vacc[i % NACC] = __fmaf_rn(sv[i], S.scale2f[i], vacc[i % NACC]);   // merging.c:431,462
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int i = HB; i < NB; i++)
+                if (!dropped.test(i)) vacc[i % NACC] = __fmaf_rn(sv[i], S.scale2f[i], vacc[i % NACC]);
+#pragma unroll
+            for (int k = 0; k < NACC; k++) vsum += (double)vacc[k];
+            } else
+#endif
+            {   // float64 products in exposure order (the MAD variant stays bit-identical to the reference)
 #pragma unroll
             for (int i = 0; i < HB; i++)
                 if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
@@ -627,6 +773,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
 #pragma unroll
             for (int i = HB; i < NB; i++)
                 if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];
+            }
         }
 #else
         if (want_var) {
@@ -665,7 +812,16 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             A.outvar[v] = ov;
             A.expmap[v] = kept;
         }
+        MB_STAMP(8);   // variance, counters, stores
     }
+#if MB_TIMING
+    __syncthreads();
+    if ((blockIdx.x == 0 || blockIdx.x == 400) && lane == 0) {
+        printf("block %d warp %d tiles %u cycles: barrier %llu issue %llu data_wait %llu pass1 %llu sort %llu clip %llu stat_issue %llu stat_wait %llu rest %llu\n",
+               (int)blockIdx.x, wib, tiles_done, sm.tph[wib][0], sm.tph[wib][1], sm.tph[wib][2], sm.tph[wib][3], sm.tph[wib][4],
+               sm.tph[wib][5], sm.tph[wib][6], sm.tph[wib][7], sm.tph[wib][8]);
+    }
+#endif
 
     // ---- flush: valid = lanes seen - invalid, selected = lanes seen - dropped -----------------
     const unsigned seen = tiles_done * 32u;

@@ -1,6 +1,7 @@
 // Launchers of the warp-tiled kernels for one stack-depth bucket; included by warp_<NB>.cu.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 
@@ -12,6 +13,7 @@ namespace mb {
 template <int NB>
 void fill_tile_args(TileArgs<NB>& s, const Job& j)
 {
+    double maxos = 0.0;
     for (int i = 0; i < NB; i++) {
         const bool in = i < j.nfiles;
         s.data[i] = in ? static_cast<const float*>(j.data[i]) : nullptr;
@@ -19,7 +21,16 @@ void fill_tile_args(TileArgs<NB>& s, const Job& j)
         s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
         s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
         s.scale2[i] = s.scale[i] * s.scale[i];
+        s.os[i] = make_double2(s.offset[i], s.scale[i]);
+        s.kscale[i] = (float)s.scale[i];
+        s.koffset[i] = (float)(s.offset[i] * s.scale[i]);
+        s.scale2f[i] = (float)s.scale2[i];
+        maxos = std::max(maxos, std::fabs(s.offset[i] * s.scale[i]));
     }
+    // key = fma(d, kscale, koffset) in float32 vs float32((offset + d) * scale): the three float32 roundings
+    // and the two rounded constants are each <= 2^-24 of (|w| + 2 |offset * scale|); the |w| part is inside
+    // the relative key margin (KEPS), the offset part is this absolute term (x2 for slack)
+    s.koff = 0x1p-20 * maxos + 0x1p-120;
     // equally spaced rows (one [N][V] allocation): the STRIDED kernels step from row to row
     auto stride_of = [&](const void* const* rows) -> unsigned {
         if (rows == nullptr || j.nfiles != NB || NB < 2) return 0u;
