@@ -33,7 +33,7 @@
 #include "sigclip_tile.cuh"
 
 #ifndef MB_WARP_THREADS
-#define MB_WARP_THREADS 128   // threads per block of the warp-tiled sigma-clip kernel
+#define MB_WARP_THREADS 0     // 0: per-depth default (WarpThreads below); otherwise threads per block of the warp kernel
 #endif
 #ifndef MB_SORT_FMA_EVERY
 #define MB_SORT_FMA_EVERY 0   // every k-th compare-exchange computes its max with 2 IMAD (FMA pipe) instead of IADD3
@@ -126,11 +126,38 @@ struct WarpSmem {
     float k[NB][32];   // sorted keys, one column per lane
 };
 
-constexpr int kWT = MB_WARP_THREADS;
+constexpr int kWT = 128;   // block size of the deep-stack kernels (sigclip_warp2.cuh, sigclip_runs.cuh)
 
-template <int NB, bool MAD = false>
+// Block size of the warp kernel.  One block per SM holding all its resident warps (768 threads at 80 registers
+// for depths <= 48): the per-tile barrier then keeps every warp of the SM in the same part of the ~45 KB loop
+// body, which exceeds the 32 KB instruction cache (measured +8 % over 128-thread blocks at N = 48, +11 % at
+// N = 12).  The MAD and TMA variants are shared-memory bound and stay at 128 threads.
+template <int NB, bool MAD, bool TMA>
+struct WarpThreads {
+    static constexpr int value = MB_WARP_THREADS ? MB_WARP_THREADS
+                                 : ((MAD || TMA) ? 128 : (NB <= 48 ? 768 : (NB <= 64 ? 512 : (NB <= 96 ? 384 : 256))));
+};
+
+// 128-byte opaque image of a CUtensorMap (filled on the host by cuTensorMapEncodeTiled)
+struct alignas(64) TensorMap2D { unsigned long long opaque[16]; };
+struct TmaMaps { TensorMap2D data, stat; };
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const TensorMap2D* map, int c0, int c1, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const TensorMap2D* map, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int NB, bool MAD = false, bool TMA = false>
 struct BlockSmem {
-    WarpSmem<NB> w[kWT / 32];
+    static constexpr int kWT = WarpThreads<NB, MAD, TMA>::value;
+    WarpSmem<NB> w[kWT / 32];                            // TMA: also the landing buffer of the DATA tile
+    float v[TMA ? kWT / 32 : 1][TMA ? NB : 1][32];       // TMA: landing buffer of the STAT tile (128-byte aligned)
+    unsigned long long bar[kWT / 32][2];                 // TMA: mbarriers of the warp's DATA / STAT tiles
     double scale[NB];
     double offset[NB];
     double rcp[NB + 1];   // 1.0 / m
@@ -315,7 +342,15 @@ struct TransposeConsts {
 };
 
 // resident 128-thread blocks per SM each depth is compiled for (register budget 65536 / (128 * blocks))
-template <int NB> struct WarpBlocks { static constexpr int value = (NB <= 48 ? MB_WARP_BLOCKS : (NB <= 64 ? 4 : (NB <= 96 ? 3 : 2))) * 128 / kWT; };
+template <int NB, int THREADS> struct WarpBlocks {
+    static constexpr int raw = (NB <= 48 ? MB_WARP_BLOCKS : (NB <= 64 ? 4 : (NB <= 96 ? 3 : 2))) * 128 / THREADS;
+    static constexpr int value = raw < 1 ? 1 : raw;
+};
+// TMA variant: two staged tiles per warp (2 x NB x 128 bytes) bound the residency, not the registers
+template <int NB, int THREADS> struct TmaBlocks {
+    static constexpr int raw = (NB <= 16 ? 8 : (NB <= 32 ? 6 : (NB <= 48 ? 4 : (NB <= 64 ? 3 : 2)))) * 128 / THREADS;
+    static constexpr int value = raw < 1 ? 1 : raw;
+};
 
 // FULL: every exposure slot is in use (nfiles == NB), so the per-row `i < nfiles` predicates and
 // selects compile away (the common case: depths 4, 8, 12, 16, 24, 32, 48, 64, 96, 128).
@@ -330,15 +365,28 @@ template <int NB> struct WarpBlocks { static constexpr int value = (NB <= 48 ? M
 // STRIDED: the rows of the stack are equally spaced in memory (one [N][V] allocation, the layout of the
 // slab slots and of any stacked tensor): row i+1 = row i + S.dstride elements, so an address costs one
 // IMAD.WIDE on the FMA pipe instead of a constant-bank load plus a 64-bit add on the ALU pipe.
-template <int NB, bool UNIT, bool FULL, bool MAD = false, bool STRIDED = false>
-__global__ void __launch_bounds__(kWT, WarpBlocks<NB>::value)
+//
+// TMA (needs STRIDED rows with a pitch and base that are multiples of 16 bytes): the [NB][32] DATA and STAT tiles
+// of a warp are fetched by ONE cp.async.bulk.tensor instruction each (2-D tensor map over [row][voxel], box
+// 32 x NB, NaN fill beyond the last voxel) into the warp's shared-memory buffers, a whole tile ahead, completion
+// on an mbarrier.  No load touches a register, no address is computed per row, and pass 1 and the variance
+// pass become short rolled loops over shared memory, so the loop body fits the 32 KB instruction cache.
+template <int NB, bool UNIT, bool FULL, bool MAD = false, bool STRIDED = false, bool TMA = false>
+__global__ void __launch_bounds__((WarpThreads<NB, MAD, TMA>::value),
+                                  (TMA ? TmaBlocks<NB, WarpThreads<NB, MAD, TMA>::value>::value : WarpBlocks<NB, WarpThreads<NB, MAD, TMA>::value>::value))
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
-                    const int flags, unsigned long long* slow_total)
+                    const int flags, unsigned long long* slow_total, const __grid_constant__ TmaMaps M)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BlockSmem<NB, MAD>& sm = *reinterpret_cast<BlockSmem<NB, MAD>*>(smem_raw);
+    BlockSmem<NB, MAD, TMA>& sm = *reinterpret_cast<BlockSmem<NB, MAD, TMA>*>(smem_raw);
+    constexpr int kWT = WarpThreads<NB, MAD, TMA>::value;
     constexpr int W = ExpSet<NB>::W;
     constexpr unsigned IDX = (1u << KeyBits<NB>::idx_bits) - 1u;
+    // Invalid samples become sentinel keys below every real key (above, for the MAD variant, whose code
+    // addresses the valid samples as [0, n)): the valid samples then end at the fixed slot NB - 1, so the
+    // largest samples -- the usual rejects -- are known by register name right after the sort.
+    constexpr bool SENT_LOW = !MAD;
+    constexpr unsigned SENT = (SENT_LOW ? 0xFF7FFFFFu : 0x7F7FFFFFu) & ~IDX;
     // key-space error model: float32 rounding + truncation of idx_bits mantissa bits is below
     // 2^-(23 - idx_bits) * 1.01 relative; the margins use four times that
     constexpr double KEPS = NB <= 64 ? 0x1p-15 : 0x1p-14;
@@ -361,7 +409,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     }
     for (int i = tid; i <= NB; i += kWT) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
 #if MB_TIMING
-    if (tid < 48) sm.tph[tid / 12][tid % 12] = 0ull;
+    for (int i = tid; i < (kWT / 32) * 12; i += kWT) sm.tph[i / 12][i % 12] = 0ull;
     long long tprev = 0;
 #endif
     __syncthreads();   // the only block-wide barrier of the kernel (unless flags & 1)
@@ -411,8 +459,30 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     // (prefetch.global.L1 only reaches L2 on this part -- tools/microbench/l1prefetch.cu: a later load still
     // takes the ~480-cycle L2 latency.  Real L1 fills, cp.async.ca of one word per sector into a dummy
     // shared-memory word, make the later load a 33-cycle L1 hit but measured 10-18 % slower here.)
-    if (tile0 + wib < ntiles) prefetch_rows(false, tile0 + wib);
-    if (want_var && (flags & 16) && tile0 + wib < ntiles) prefetch_rows(true, tile0 + wib);
+    unsigned tma_phase = 0u;
+    constexpr unsigned kTileBytes = NB * 32 * sizeof(float);
+    // one lane requests a tile: both boxes land in the warp's buffers, each completes its own mbarrier
+    auto tma_request = [&](long long t) {
+        mbar_expect_tx(&sm.bar[wib][0], kTileBytes);
+        tma_load_2d(&sm.w[wib].k[0][0], &M.data, (int)(t << 5), 0, &sm.bar[wib][0]);
+        if (want_var) {
+            mbar_expect_tx(&sm.bar[wib][1], kTileBytes);
+            tma_load_2d(&sm.v[TMA ? wib : 0][0][0], &M.stat, (int)(t << 5), 0, &sm.bar[wib][1]);
+        }
+    };
+    if constexpr (TMA) {
+        if (lane == 0) {
+            mbar_init(&sm.bar[wib][0], 1);
+            mbar_init(&sm.bar[wib][1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tile0 + wib < ntiles) tma_request(tile0 + wib);
+        }
+        __syncwarp();
+    } else {
+        if (tile0 + wib < ntiles) prefetch_rows(false, tile0 + wib);
+        if (want_var && (flags & 16) && tile0 + wib < ntiles) prefetch_rows(true, tile0 + wib);
+    }
 
     // The trip count is uniform per block so that the optional per-tile barrier is legal; a warp
     // whose last tile lies beyond the range runs it with every lane idle.
@@ -423,102 +493,171 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         const long long tile = tile0 + wib;
         const long long v = (tile << 5) + lane;
         const bool act = tile < ntiles && v < A.nvox;
-        if (want_var && (flags & 8)) prefetch_rows(true, tile);   // flags & 8: STAT prefetch at tile start (3 % slower)
+        if (!TMA && want_var && (flags & 8)) prefetch_rows(true, tile);   // flags & 8: STAT prefetch at tile start (3 % slower)
 
-        // ---- gather: one coalesced load per exposure ------------------------------------------
         float key[NB];
+        ExpSet<NB> inval;
+        double sum = 0.0, p = 0.0, T1 = 0.0, S2 = 0.0;
+        if constexpr (!TMA) {
+            // ---- gather: one coalesced load per exposure ------------------------------------------
 #if MB_ABLATE   // tuning builds: flags & 32 gathers from an L1-resident window (LSU work without L2 / DRAM)
-        const float* rp = (flags & 32) ? S.data[0] + (v & 1023) : S.data[0] + v;
-        const unsigned gstride = (flags & 32) ? 32u : S.dstride;
+            const float* rp = (flags & 32) ? S.data[0] + (v & 1023) : S.data[0] + v;
+            const unsigned gstride = (flags & 32) ? 32u : S.dstride;
 #else
-        const float* rp = S.data[0] + v;
-        const unsigned gstride = S.dstride;
+            const float* rp = S.data[0] + v;
+            const unsigned gstride = S.dstride;
 #endif
 #pragma unroll
-        for (int i = 0; i < NB; i++) {
-            // predicated loads: ptxas keeps them batched at the top of the tile (unconditional
-            // ones get sunk next to their first use and their latency serialises)
-            key[i] = CUDART_NAN_F;
-            if constexpr (STRIDED) {
-                if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(rp));
-                asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(rp) : "r"(gstride));
-            } else {
-                if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
+            for (int i = 0; i < NB; i++) {
+                // predicated loads: ptxas keeps them batched at the top of the tile (unconditional
+                // ones get sunk next to their first use and their latency serialises)
+                key[i] = CUDART_NAN_F;
+                if constexpr (STRIDED) {
+                    if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(rp));
+                    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(rp) : "r"(gstride));
+                } else {
+                    if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
+                }
             }
-        }
-        asm volatile("" ::: "memory");
-        // next tile's DATA rows into L1: issued behind the gather so that its address loads overlap the gather latency
-        if (tile + wstride < ntiles && !(MB_ABLATE && (flags & 128))) prefetch_rows(false, tile + wstride);
-        if (want_var && (flags & 16) && tile + wstride < ntiles) prefetch_rows(true, tile + wstride);   // flags & 16: STAT a tile ahead as well
-        MB_STAMP(1);   // gather + prefetch issue
+            asm volatile("" ::: "memory");
+            // next tile's DATA rows into L1: issued behind the gather so that its address loads overlap the gather latency
+            if (tile + wstride < ntiles && !(MB_ABLATE && (flags & 128))) prefetch_rows(false, tile + wstride);
+            if (want_var && (flags & 16) && tile + wstride < ntiles) prefetch_rows(true, tile + wstride);   // flags & 16: STAT a tile ahead as well
+            MB_STAMP(1);   // gather + prefetch issue
 #if MB_TIMING
 #pragma unroll
-        for (int i = 0; i < NB; i++) MB_TOUCH(key[i]);
+            for (int i = 0; i < NB; i++) MB_TOUCH(key[i]);
 #endif
-        MB_STAMP(2);   // DATA arrival
+            MB_STAMP(2);   // DATA arrival
 
-        // ---- pass 1: exposure order.  w, shifted moments, keys ----------------------------------
-        // Straight-line, 11-12 instructions per exposure: one conversion, (offset + d) * scale exactly as
-        // merging.c:426, t = w - p, and one PTX block that does everything depending on "d is not NaN"
-        // under a predicate (moment updates, invalid bit, sentinel select) -- no branch per exposure.
-        ExpSet<NB> inval;
-        // MB_P1_CHAINS independent accumulator chains: the 48-deep dependent chains of float64 adds were the
-        // critical path of this pass (the pipe has a long latency and only six warps share a scheduler)
-        constexpr int NCH = MB_P1_CHAINS;
-        double sum = 0.0, p = 0.0, T1c[NCH], S2c[NCH];
+            // ---- pass 1: exposure order.  w, shifted moments, keys ----------------------------------
+            // Straight-line, 11-12 instructions per exposure: one conversion, (offset + d) * scale exactly as
+            // merging.c:426, t = w - p, and one PTX block that does everything depending on "d is not NaN"
+            // under a predicate (moment updates, invalid bit, sentinel select) -- no branch per exposure.
+            // MB_P1_CHAINS independent accumulator chains: the 48-deep dependent chains of float64 adds were the
+            // critical path of this pass (the pipe has a long latency and only six warps share a scheduler)
+            constexpr int NCH = MB_P1_CHAINS;
+            double T1c[NCH], S2c[NCH];
 #pragma unroll
-        for (int c = 0; c < NCH; c++) { T1c[c] = 0.0; S2c[c] = 0.0; }
-        bool have_p = false;
+            for (int c = 0; c < NCH; c++) { T1c[c] = 0.0; S2c[c] = 0.0; }
+            bool have_p = false;
 #pragma unroll
-        for (int i = 0; i < NB; i++) {
-            const float d = key[i];
-            const unsigned sentinel = (0x7F7FFFFFu & ~IDX) | (unsigned)i;
-            double w;
-            float kf;
-            if constexpr (UNIT) {
-                w = (double)d;
-                kf = d;
-            } else {
-                w = (S.os[i].x + (double)d) * S.os[i].y;
+            for (int i = 0; i < NB; i++) {
+                const float d = key[i];
+                const unsigned sentinel = SENT | (unsigned)i;
+                double w;
+                float kf;
+                if constexpr (UNIT) {
+                    w = (double)d;
+                    kf = d;
+                } else {
+                    w = (S.os[i].x + (double)d) * S.os[i].y;
 #if MB_KEY_FFMA
-                kf = __fmaf_rn(d, S.kscale[i], S.koffset[i]);
+                    kf = __fmaf_rn(d, S.kscale[i], S.koffset[i]);
 #else
-                kf = __double2float_rn(w);
+                    kf = __double2float_rn(w);
 #endif
-            }
-            if (i < 4) {                       // pivot = first valid sample among the first four
+                }
+                if (i < 4) {                       // pivot = first valid sample among the first four
+                    const bool ok = (d == d);
+                    p = (ok && !have_p) ? w : p;
+                    have_p = have_p || ok;
+                }
                 const bool ok = (d == d);
+                // invalid sample: t becomes a denormal (high word cleared, at most 2^-1042 in magnitude) with ONE
+                // select; the unconditional moment updates below then add nothing that survives a rounding
+                double t = w - p;
+                t = __hiloint2double(ok ? __double2hiint(t) : 0, __double2loint(t));
+#if MB_EXACT_SUM
+                sum += ok ? w : 0.0;               // tools.c:13-16, exposure order, no FMA
+#endif
+                T1c[i % NCH] += t;
+                S2c[i % NCH] = __fma_rn(t, t, S2c[i % NCH]);
+                if (!ok) inval.set(i);
+                const unsigned kb = (__float_as_uint(kf) & keep_mask) | (unsigned)i;
+                key[i] = __uint_as_float(ok ? kb : sentinel);
+            }
+            T1 = T1c[0]; S2 = S2c[0];
+#pragma unroll
+            for (int c = 1; c < NCH; c++) { T1 += T1c[c]; S2 += S2c[c]; }
+        } else {
+            // ---- TMA path: the DATA tile is (or is about to be) in the warp's key column ------------------
+            if (!(tile < ntiles)) continue;                    // no tile, nothing was requested
+            if (lane == 0 && tile + wstride < ntiles) {        // L2 prefetch of the tile after this one
+                tma_prefetch_2d(&M.data, (int)((tile + wstride) << 5), 0);
+                if (want_var) tma_prefetch_2d(&M.stat, (int)((tile + wstride) << 5), 0);
+            }
+            mbar_wait(&sm.bar[wib][0], tma_phase);
+            MB_STAMP(2);
+            // pivot = first valid sample among the first four (tools.c sums are order-sensitive, the pivot is not)
+            bool have_p = false;
+#pragma unroll
+            for (int i = 0; i < 4 && i < NB; i++) {
+                const float d = sk[i][lane];
+                const bool ok = (d == d);
+                const double w = UNIT ? (double)d : (S.os[i].x + (double)d) * S.os[i].y;
                 p = (ok && !have_p) ? w : p;
                 have_p = have_p || ok;
             }
-            const bool ok = (d == d);
-            // invalid sample: t becomes a denormal (high word cleared, at most 2^-1042 in magnitude) with ONE
-            // select; the unconditional moment updates below then add nothing that survives a rounding
-            double t = w - p;
-            t = __hiloint2double(ok ? __double2hiint(t) : 0, __double2loint(t));
-#if MB_EXACT_SUM
-            sum += ok ? w : 0.0;               // tools.c:13-16, exposure order, no FMA
-#endif
-            T1c[i % NCH] += t;
-            S2c[i % NCH] = __fma_rn(t, t, S2c[i % NCH]);
-            if (!ok) inval.set(i);
-            const unsigned kb = (__float_as_uint(kf) & keep_mask) | (unsigned)i;
-            key[i] = __uint_as_float(ok ? kb : sentinel);
-        }
-        double T1 = T1c[0], S2 = S2c[0];
+            // pass 1 as a rolled loop over the staged rows; the key replaces the sample in place
 #pragma unroll
-        for (int c = 1; c < NCH; c++) { T1 += T1c[c]; S2 += S2c[c]; }
+            for (int wd = 0; wd < W; wd++) {
+                unsigned bad = 0u;
+                const int hi = (wd + 1) * 32 < NB ? (wd + 1) * 32 : NB;
+#pragma unroll 4
+                for (int i = wd * 32; i < hi; i++) {
+                    const float d = sk[i][lane];
+                    const bool ok = (d == d);
+                    double w;
+                    float kf;
+                    if constexpr (UNIT) {
+                        w = (double)d;
+                        kf = d;
+                    } else {
+                        const double2 os = S.os[i];
+                        w = (os.x + (double)d) * os.y;            // merging.c:426
+                        kf = __double2float_rn(w);
+                    }
+                    double t = w - p;
+                    t = __hiloint2double(ok ? __double2hiint(t) : 0, __double2loint(t));
+                    sum += ok ? w : 0.0;                          // tools.c:13-16, exposure order, no FMA
+                    T1 += t;
+                    S2 = __fma_rn(t, t, S2);
+                    bad |= ok ? 0u : (1u << (i & 31));
+                    const unsigned kb = (__float_as_uint(kf) & keep_mask) | (unsigned)i;
+                    sk[i][lane] = __uint_as_float(ok ? kb : (SENT | (unsigned)i));
+                }
+                inval.w[wd] = bad;
+            }
+#pragma unroll
+            for (int q = 0; q < NB; q++) key[q] = sk[q][lane];
+        }
         const int n = NB - inval.count();
+        float dspec[2] = {0.f, 0.f};
         MB_STAMP(3);   // pass 1
 
         if (!(flags & 4)) {   // flags & 4: timing experiment only (skips the sort and the clip loop; wrong results)
         sort_keys_mixed<NB, MB_SORT_FMA_EVERY>(key, one, minus_one);
+        // speculative exact lookups of the two largest samples (L1 / L2 hits), in flight while sigma,
+        // median and bounds are computed: a rejected sample's exact value is then usually already here
+        if constexpr (SENT_LOW) {
+            if (n >= 2 && act) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int i = (int)(__float_as_uint(key[NB - 1 - j]) & IDX);
+                    const float* src;
+                    if constexpr (STRIDED) src = S.data[0] + (size_t)i * S.dstride + v;
+                    else src = sm.data[i] + v;
+                    dspec[j] = __ldg(src);
+                }
+            }
+        }
 #pragma unroll
         for (int q = 0; q < NB; q++) sk[q][lane] = key[q];
         }
         // the STAT rows are prefetched into L1 only now: close enough to their use (after the clip
         // loop) that they are still there, early enough that the latency is covered
-        if (want_var && !(flags & (8 | 16)) && !(MB_ABLATE && (flags & 128))) prefetch_rows(true, tile);
+        if (!TMA && want_var && !(flags & (8 | 16)) && !(MB_ABLATE && (flags & 128))) prefetch_rows(true, tile);
         MB_STAMP(4);   // sort + column store + STAT prefetch
 
 #if !MB_LATE_STAT
@@ -541,7 +680,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         double mean = n > 0 ? p + T1 * sm.rcp[n] : CUDART_NAN;
 #endif
         double sigma = 0.0;
-        int a = 0, b = n;
+        int a = SENT_LOW ? NB - n : 0, b = a + n;   // window of the valid samples in the sorted column
         ExpSet<NB> rejected;
         bool slow = false;
         if constexpr (MAD) {
@@ -637,11 +776,41 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 // keys certainly at or below the low bound / certainly below the high bound
                 const float f_lo_in = __double2float_ru(clo + T), f_lo_out = __double2float_rd(clo - T);
                 const float f_up_in = __double2float_rd(cup - T), f_up_out = __double2float_ru(cup + T);
-                int lo_in = count_col<NB, true>(sk, lane, f_lo_in);
-                int up_in = count_col<NB, false>(sk, lane, f_up_in);
+                // The rejected samples are almost always the last few keys at either end of the window: probe
+                // four keys per end (eight independent loads) instead of two dependent binary searches; only a
+                // lane with four or more rejections on one side falls back to the search.
+                float kl4[4], ku4[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int ql = a + j, qu = b - 1 - j;
+                    kl4[j] = ql < b ? sk[ql < NB ? ql : NB - 1][lane] : CUDART_INF_F;
+                    ku4[j] = qu >= a ? sk[qu >= 0 ? qu : 0][lane] : -CUDART_INF_F;
+                }
+                int jl = 0, ju = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    jl += (jl == j && kl4[j] <= f_lo_in) ? 1 : 0;        // leading keys possibly at or below the low bound
+                    ju += (ju == j && !(ku4[j] < f_up_in)) ? 1 : 0;      // trailing keys not certainly below the high bound
+                }
+                int lo_in, up_in;
+                bool lo_band, up_band;
                 // band checks: no key in (clo - T, clo + T] and none in [cup - T, cup + T)
-                const bool lo_band = lo_in > 0 && !(sk[lo_in - 1][lane] <= f_lo_out);
-                const bool up_band = up_in < NB && (sk[up_in < NB ? up_in : NB - 1][lane] < f_up_out);
+                if (jl < 4) {
+                    lo_in = a + jl;
+                    const float last = jl == 3 ? kl4[2] : (jl == 2 ? kl4[1] : kl4[0]);
+                    lo_band = jl > 0 && !(last <= f_lo_out);
+                } else {
+                    lo_in = count_col<NB, true>(sk, lane, f_lo_in);
+                    lo_band = lo_in > 0 && !(sk[lo_in - 1][lane] <= f_lo_out);
+                }
+                if (ju < 4) {
+                    up_in = b - ju;
+                    const float first = ju == 3 ? ku4[2] : (ju == 2 ? ku4[1] : ku4[0]);
+                    up_band = ju > 0 && (first < f_up_out);
+                } else {
+                    up_in = count_col<NB, false>(sk, lane, f_up_in);
+                    up_band = up_in < NB && (sk[up_in < NB ? up_in : NB - 1][lane] < f_up_out);
+                }
                 if (lo_band || up_band) {
                     // ~1e-4 of the voxels: settle the band keys from their exact values
                     if (!refine_band<NB, UNIT>(sk, lane, sm.data, v, sm.scale, sm.offset, ih, il, m, sigma, A.nclip_low,
@@ -670,8 +839,9 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                         const float* src;
                         if constexpr (STRIDED) src = S.data[0] + (size_t)iv[j] * S.dstride + v;
                         else src = sm.data[iv[j]] + v;
-                        dv[j] = 0.f;
-                        if (k < r) dv[j] = __ldg(src);
+                        const bool spec = SENT_LOW && q >= NB - 2;     // one of the two speculative lookups
+                        dv[j] = spec ? (q == NB - 1 ? dspec[0] : dspec[1]) : 0.f;
+                        if (k < r && !spec) dv[j] = __ldg(src);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
@@ -710,6 +880,42 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         // STAT rows loaded only now (prefetched into L1 after the sort): fewer live registers across the
         // clip loop, more resident blocks per SM.  Two half-batches: the second is in flight while the
         // first is consumed.
+        if constexpr (TMA) {
+            if (want_var) {
+                // the STAT tile arrived long ago (requested with the DATA tile); rolled loop, NACC float32 chains
+                mbar_wait(&sm.bar[wib][1], tma_phase);
+                MB_STAMP(7);   // STAT arrival
+                constexpr int NACC = (NB % 8 == 0) ? 8 : 4;
+                float vacc[NACC];
+#pragma unroll
+                for (int k = 0; k < NACC; k++) vacc[k] = 0.f;
+                const float (*sv)[32] = sm.v[TMA ? wib : 0];
+#pragma unroll
+                for (int wd = 0; wd < W; wd++) {
+                    const unsigned gone = dropped.w[wd];
+                    const int hi = (wd + 1) * 32 < NB ? (wd + 1) * 32 : NB;
+                    for (int i0 = wd * 32; i0 < hi; i0 += NACC) {
+#pragma unroll
+                        for (int j = 0; j < NACC; j++) {
+                            const int i = i0 + j;
+                            const float x = sv[i][lane];
+                            if (!((gone >> (i & 31)) & 1u)) vacc[j] = __fmaf_rn(x, S.scale2f[i], vacc[j]);   // merging.c:431,462
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NACC; k++) vsum += (double)vacc[k];
+            }
+            // both buffers are free: request the warp's next tile (generic-proxy accesses first made visible
+            // to the async proxy), then flip the parity the next waits will look for
+            __syncwarp();
+            if (lane == 0 && tile + wstride < ntiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                tma_request(tile + wstride);
+            }
+            tma_phase ^= 1u;
+            MB_STAMP(6);   // variance loop + next request
+        } else {
         float sv[NB];
         if (want_var) {
             const long long vs = act ? v : A.nvox - 1;
@@ -775,7 +981,9 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];
             }
         }
+        }   // !TMA
 #else
+        static_assert(!TMA, "the TMA variant needs MB_LATE_STAT");
         if (want_var) {
 #pragma unroll
             for (int i = 0; i < NB; i++)

@@ -400,3 +400,32 @@ def test_equally_spaced_and_scattered_rows_agree(n):
             assert_same_result(b, want)
             for key in ("data", "var", "expmap", "select_pix", "valid_pix"):
                 np.testing.assert_array_equal(a[key], b[key])
+
+
+def test_tma_variant_in_a_fresh_process():
+    """The opt-in TMA-staged variant (MPDAF_B200_TMA=1, read once per process) gives the same results."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import numpy as np, oracle, cuda_runner
+from helpers import random_stack, assert_same_result
+rng = np.random.default_rng(11)
+seen = set()
+for n in (8, 12, 24, 48, 64, 96):
+    data, var = random_stack(rng, n, (4, 32, 33), nan_frac=0.1, outlier_frac=0.05)   # 4224 voxels, 16-byte pitch
+    for kw in (dict(), dict(scales=np.linspace(.9, 1.1, n), offsets=np.linspace(-.1, .1, n))):
+        for vt, nclip in (('propagate', 3.0), ('stat_mean', 5.0)):
+            got = cuda_runner.combine_cuda(data, var, nclip=nclip, vartype=vt, location='device_stacked', **kw)
+            assert_same_result(got, oracle.combine_port(data, var, nclip=nclip, vartype=vt, **kw))
+            seen.add(cuda_runner.kernel_name())
+assert all('tma' in k for k in seen), seen
+print('tma ok', sorted(seen))
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MPDAF_B200_TMA="1")
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "tma ok" in res.stdout
