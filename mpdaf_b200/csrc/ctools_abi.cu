@@ -253,10 +253,10 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         int rc = MPDAF_B200_ERR_ARG;
         const bool no_two_run = std::getenv("MPDAF_B200_NO_TWO_RUN") != nullptr;
         const bool force_two_run = std::getenv("MPDAF_B200_TWO_RUN") != nullptr;   // read per call (tests toggle it)
-        // two sorted runs (sigclip_warp2.cuh): measured faster than the single 128-key network only when
-        // scales/offsets are in play (that network spills at 255 registers); MPDAF_B200_TWO_RUN=1 forces it
-        // for every stack deeper than 64
-        if (!j.median && !j.a.mad && nb > 64 && !no_two_run && (force_two_run || (nb == 128 && !unit))) {
+        // two sorted runs (sigclip_warp2.cuh): was the faster kernel for N = 128 with scales/offsets until the
+        // single-network kernel got its lean pass 1 and 256-thread blocks (now 2.34 vs 5.15 ms for 32 planes);
+        // kept as a cross-check, MPDAF_B200_TWO_RUN=1 selects it for every stack deeper than 64
+        if (!j.median && !j.a.mad && nb > 64 && !no_two_run && force_two_run) {
             rc = upload_table(j, stream);
             if (rc == MPDAF_B200_OK) rc = nb == 96 ? mb_launch_warp2_48(j, unit, ctx) : mb_launch_warp2_64(j, unit, ctx);
             g_last_kernel = name;
