@@ -265,6 +265,8 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at the default debug level; stdout carries the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
 
     nz = pick_nz(torch, dev, args.nz)
