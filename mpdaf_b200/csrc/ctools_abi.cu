@@ -413,7 +413,7 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     // chunk: bounded staging per slot (default 128 MiB of samples: small enough that the copy
     // of one chunk overlaps the kernel of the previous one even for short stacks, large enough
     // that every per-exposure segment is a ~MB-sized copy), multiple of 1024 voxels
-    const long long budget = env_ll("MPDAF_B200_SLAB_BYTES", 128LL << 20);
+    const long long budget = env_ll("MPDAF_B200_SLAB_BYTES", from_files ? 128LL << 20 : 256LL << 20);
     long long chunk = budget / ((long long)planes * esz);
     chunk = std::max(1024LL, chunk / 1024 * 1024);
     chunk = std::min(chunk, (nvox + 1023) / 1024 * 1024);
@@ -424,6 +424,21 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     for (int k = 0; k < nslots; k++) {
         const int rc0 = ensure_slot(slots[k], (size_t)planes * chunk * esz, (size_t)chunk, from_files);
         if (rc0 != MPDAF_B200_OK) return rc0;
+    }
+
+    // byte distance between consecutive host rows when it is the same for all of them (else 0): [0] DATA, [1] STAT
+    long long host_pitch[2] = {0, 0};
+    if (!from_files) {
+        auto pitch_of = [&](const void* const* rows) -> long long {
+            if (rows == nullptr || nfiles < 2) return 0;
+            const long long step = (const char*)rows[1] - (const char*)rows[0];
+            if (step < nvox * (long long)esz || step > 0x7FFFFFFFLL) return 0;      // cudaMemcpy2D pitches are below 2 GiB
+            for (int i = 2; i < nfiles; i++)
+                if ((const char*)rows[i] - (const char*)rows[i - 1] != step) return 0;
+            return step;
+        };
+        host_pitch[0] = pitch_of(src.host_data);
+        host_pitch[1] = need_var ? pitch_of(src.host_var) : 0;
     }
 
     int rc = MPDAF_B200_OK;
@@ -479,12 +494,23 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
             }
             g_last_launches++;
         } else {
-            for (int p = 0; p < planes && rc == MPDAF_B200_OK; p++) {
-                const char* base = (const char*)(p < nfiles ? src.host_data[p] : src.host_var[p - nfiles]);
-                if (cudaMemcpyAsync(s.d_in + (size_t)p * chunk * esz, base + (size_t)v0 * esz, (size_t)cnt * esz,
-                                    cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
-                    rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a host slab failed");
-            }
+            // equally spaced host rows (one [N][V] array): ONE 2-D copy per chunk for DATA and one for STAT instead
+            // of a copy per exposure (measured 45.6 -> 50+ GB/s at 128 MiB chunks; the box's plain H2D rate is 55.5)
+            auto copy_rows = [&](const void* const* rows, int first_plane) -> bool {
+                const long long pitch = host_pitch[first_plane ? 1 : 0];
+                if (pitch > 0) {
+                    return cudaMemcpy2DAsync(s.d_in + (size_t)first_plane * chunk * esz, (size_t)chunk * esz,
+                                             (const char*)rows[0] + (size_t)v0 * esz, (size_t)pitch, (size_t)cnt * esz,
+                                             (size_t)nfiles, cudaMemcpyHostToDevice, s.stream) == cudaSuccess;
+                }
+                for (int p = 0; p < nfiles; p++)
+                    if (cudaMemcpyAsync(s.d_in + (size_t)(first_plane + p) * chunk * esz, (const char*)rows[p] + (size_t)v0 * esz,
+                                        (size_t)cnt * esz, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+                        return false;
+                return true;
+            };
+            if (!copy_rows(src.host_data, 0) || (need_var && !copy_rows(src.host_var, nfiles)))
+                rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a host slab failed");
             if (rc != MPDAF_B200_OK) break;
         }
 
