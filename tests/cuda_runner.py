@@ -36,10 +36,15 @@ def combine_cuda(data, var=None, scales=None, offsets=None, nmax=2, nclip=5.0, n
     sp = None if scale is None else scale.ctypes.data
     op = None if offset is None else offset.ctypes.data
     params = (int(nmax), float(lo), float(up), int(nstop), int(_typ(vartype)), int(mad))
-    if location == "host":
+    if location in ("host", "host_stacked"):
         out = np.empty(nvox)
         outvar = np.empty(nvox)
         expmap = np.empty(nvox, dtype=np.intc)
+        if location == "host_stacked":     # one [N][V] array per HDU: equally spaced rows -> one 2-D copy per chunk
+            sd = np.stack([a.reshape(-1) for a in data])
+            sv = None if var is None else np.stack([a.reshape(-1) for a in var])
+            data = list(sd)
+            var = None if sv is None else list(sv)
         kd, dptr = _table([a.ctypes.data for a in data])
         kv, vptr = (None, None) if var is None else _table([a.ctypes.data for a in var])
         rc = ctools.mpdaf_b200_sigma_clipping_arrays(

@@ -429,3 +429,22 @@ print('tma ok', sorted(seen))
     res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "tma ok" in res.stdout
+
+
+@pytest.mark.parametrize("n", [3, 12, 48])
+def test_host_rows_in_one_array_use_2d_copies(n, monkeypatch):
+    """HOST location with equally spaced rows (one [N][V] array: a single 2-D copy per chunk) gives the same
+    result as separate arrays (one copy per exposure), also when the stack takes several chunks."""
+    rng = np.random.default_rng(200 + n)
+    data, var = random_stack(rng, n, (9, 17, 23), nan_frac=0.1, outlier_frac=0.05)   # 3519 voxels
+    kw = dict(scales=np.linspace(0.9, 1.1, n), offsets=np.linspace(-0.1, 0.1, n), nclip=3.0)
+    want = oracle.combine_port(data, var, **kw)
+    for budget in (None, str(1024 * 2 * n * 4)):           # default chunking, then 1024-voxel chunks
+        if budget is not None:
+            monkeypatch.setenv("MPDAF_B200_SLAB_BYTES", budget)
+        a = cuda().combine_cuda(data, var, location="host", **kw)
+        b = cuda().combine_cuda(data, var, location="host_stacked", **kw)
+        assert_same_result(a, want)
+        assert_same_result(b, want)
+        for key in ("data", "var", "expmap", "select_pix", "valid_pix"):
+            np.testing.assert_array_equal(a[key], b[key])
