@@ -341,6 +341,10 @@ struct Slot {
     double* d_var = nullptr;
     int* d_exp = nullptr;
     char* h_in = nullptr;      // pinned staging for file reads
+    char* h_out = nullptr;     // pinned staging for results bound for pageable caller buffers: [data f64][var f64][expmap i32]
+    size_t h_out_cap = 0;      // voxels
+    long long pend_v0 = 0, pend_cnt = 0;   // chunk waiting in h_out for its copy into the caller's buffers
+    bool pending = false;
     StackTable* d_table = nullptr;
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     bool timed = false;
@@ -383,7 +387,30 @@ int ensure_slot(Slot& s, size_t in_bytes, size_t chunk, bool host_staging)
         s.host_bytes = in_bytes;
     }
     s.timed = false;
+    s.pending = false;
     return MPDAF_B200_OK;
+}
+
+int ensure_out_staging(Slot& s, size_t chunk)
+{
+    if (chunk > s.h_out_cap) {
+        if (s.h_out) cudaFreeHost(s.h_out);
+        s.h_out_cap = 0;
+        MB_CUDA(cudaMallocHost(&s.h_out, chunk * (2 * sizeof(double) + sizeof(int))));
+        s.h_out_cap = chunk;
+    }
+    return MPDAF_B200_OK;
+}
+
+// true when the pointer is page-locked host memory the copy engines can write asynchronously
+bool is_pinned_host(const void* p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
 }
 
 struct SlabSource {
@@ -420,9 +447,12 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     if (chunk < 1) chunk = 1024;
     const int nslots = (int)std::max<long long>(1, std::min<long long>(kSlots, (nvox + chunk - 1) / chunk));
 
+    // pageable host arrays (plain NumPy) are gathered into the slot's pinned staging by worker threads, like file
+    // reads: a copy engine reading pageable memory goes through the driver's own single staging buffer and blocks
+    const bool stage_in = from_files || !(is_pinned_host(src.host_data[0]) && (!need_var || is_pinned_host(src.host_var[0])));
     Slot* slots = g_slots[device];
     for (int k = 0; k < nslots; k++) {
-        const int rc0 = ensure_slot(slots[k], (size_t)planes * chunk * esz, (size_t)chunk, from_files);
+        const int rc0 = ensure_slot(slots[k], (size_t)planes * chunk * esz, (size_t)chunk, stage_in);
         if (rc0 != MPDAF_B200_OK) return rc0;
     }
 
@@ -441,6 +471,25 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         host_pitch[1] = need_var ? pitch_of(src.host_var) : 0;
     }
 
+    // Results bound for pageable buffers (plain NumPy arrays: what ctools.py passes) go through pinned staging
+    // and are copied out by this thread when the slot comes round again: a D2H copy straight into pageable
+    // memory blocks the thread until the chunk's kernel has finished, which serialises read / H2D / kernel / D2H
+    const bool stage_out = !(is_pinned_host(out) && (job.median || is_pinned_host(outvar)) && is_pinned_host(expmap));
+    if (stage_out)
+        for (int k = 0; k < nslots; k++) {
+            const int rc0 = ensure_out_staging(slots[k], (size_t)chunk);
+            if (rc0 != MPDAF_B200_OK) return rc0;
+        }
+    auto drain = [&](Slot& s) {
+        if (!s.pending) return;
+        const size_t cap = s.h_out_cap;
+        const double* hd = reinterpret_cast<const double*>(s.h_out);
+        std::memcpy(out + s.pend_v0, hd, (size_t)s.pend_cnt * sizeof(double));
+        if (!job.median) std::memcpy(outvar + s.pend_v0, hd + cap, (size_t)s.pend_cnt * sizeof(double));
+        std::memcpy(expmap + s.pend_v0, s.h_out + 2 * cap * sizeof(double), (size_t)s.pend_cnt * sizeof(int));
+        s.pending = false;
+    };
+
     int rc = MPDAF_B200_OK;
     double kernel_ms = 0.0;
     std::vector<const void*> dptr(planes);
@@ -450,6 +499,7 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         const long long cnt = std::min(chunk, nvox - v0);
         // the slot's previous chunk must have left the device (and its pinned staging)
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { rc = fail(MPDAF_B200_ERR_CUDA, "slab stream failed"); break; }
+        drain(s);
         if (s.timed) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, s.k0, s.k1);
@@ -458,8 +508,8 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         }
         for (int p = 0; p < planes; p++) dptr[p] = s.d_in + (size_t)p * chunk * esz;
 
-        if (from_files) {
-            // parallel pread of every exposure's byte range into pinned staging
+        if (stage_in) {
+            // parallel pread (files) or memcpy (pageable arrays) of every exposure's range into pinned staging
             std::atomic<int> next{0}, bad{0};
             std::string first_err;
             std::mutex err_mutex;
@@ -467,6 +517,11 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
                 for (;;) {
                     const int p = next.fetch_add(1);
                     if (p >= planes) return;
+                    if (!from_files) {
+                        const char* base = (const char*)(p < nfiles ? src.host_data[p] : src.host_var[p - nfiles]);
+                        std::memcpy(s.h_in + (size_t)p * chunk * esz, base + (size_t)v0 * esz, (size_t)cnt * esz);
+                        continue;
+                    }
                     const mbfits::ImageHdu& h = p < nfiles ? (*src.fits_data)[p] : (*src.fits_var)[p - nfiles];
                     std::string err;
                     if (mbfits::read_raw(h, v0, cnt, s.h_in + (size_t)p * chunk * esz, &err) != MPDAF_B200_OK) {
@@ -482,17 +537,19 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
             for (auto& t : pool) t.join();
             if (bad.load()) { rc = fail(MPDAF_B200_ERR_IO, first_err); break; }
             if (cudaMemcpyAsync(s.d_in, s.h_in, (size_t)planes * chunk * esz, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) {
-                rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a FITS slab failed");
+                rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a staged slab failed");
                 break;
             }
-            const long long words = (long long)planes * chunk * (esz / 4);
-            // FITS is big-endian: swap 32-bit words (for f64 the word pair is swapped by the 64-bit variant)
-            if (esz == 4) {
-                bswap32_kernel<<<1024, 256, 0, s.stream>>>((uint32_t*)s.d_in, words);
-            } else {
-                bswap64_kernel<<<1024, 256, 0, s.stream>>>((unsigned long long*)s.d_in, (long long)planes * chunk);
+            if (from_files) {
+                const long long words = (long long)planes * chunk * (esz / 4);
+                // FITS is big-endian: swap 32-bit words (for f64 the word pair is swapped by the 64-bit variant)
+                if (esz == 4) {
+                    bswap32_kernel<<<1024, 256, 0, s.stream>>>((uint32_t*)s.d_in, words);
+                } else {
+                    bswap64_kernel<<<1024, 256, 0, s.stream>>>((unsigned long long*)s.d_in, (long long)planes * chunk);
+                }
+                g_last_launches++;
             }
-            g_last_launches++;
         } else {
             // equally spaced host rows (one [N][V] array): ONE 2-D copy per chunk for DATA and one for STAT instead
             // of a copy per exposure (measured 45.6 -> 50+ GB/s at 128 MiB chunks; the box's plain H2D rate is 55.5)
@@ -527,16 +584,26 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         if (rc != MPDAF_B200_OK) break;
         cudaEventRecord(s.k1, s.stream);
         s.timed = true;
-        bool ok = cudaMemcpyAsync(out + v0, s.d_out, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+        double* to_data = stage_out ? reinterpret_cast<double*>(s.h_out) : out + v0;
+        double* to_var = stage_out ? reinterpret_cast<double*>(s.h_out) + s.h_out_cap : outvar + v0;
+        int* to_exp = stage_out ? reinterpret_cast<int*>(s.h_out + 2 * s.h_out_cap * sizeof(double)) : expmap + v0;
+        bool ok = cudaMemcpyAsync(to_data, s.d_out, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
         if (!job.median)
-            ok = ok && cudaMemcpyAsync(outvar + v0, s.d_var, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
-        ok = ok && cudaMemcpyAsync(expmap + v0, s.d_exp, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+            ok = ok && cudaMemcpyAsync(to_var, s.d_var, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
+        ok = ok && cudaMemcpyAsync(to_exp, s.d_exp, (size_t)cnt * sizeof(int), cudaMemcpyDeviceToHost, s.stream) == cudaSuccess;
         if (!ok) rc = fail(MPDAF_B200_ERR_CUDA, "D2H of a result slab failed");
+        if (stage_out && ok) {
+            s.pend_v0 = v0;
+            s.pend_cnt = cnt;
+            s.pending = true;
+        }
     }
     for (int k = 0; k < nslots; k++) {
         Slot& s = slots[k];
         if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc == MPDAF_B200_OK)
             rc = fail(MPDAF_B200_ERR_CUDA, std::string("slab pipeline: ") + cudaGetErrorString(cudaGetLastError()));
+        if (rc == MPDAF_B200_OK) drain(s);
+        s.pending = false;
         if (s.timed) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, s.k0, s.k1);
