@@ -128,14 +128,14 @@ struct WarpSmem {
 
 constexpr int kWT = 128;   // block size of the deep-stack kernels (sigclip_warp2.cuh, sigclip_runs.cuh)
 
-// Block size of the warp kernel.  One block per SM holding all its resident warps (768 threads at 80 registers
-// for depths <= 48): the per-tile barrier then keeps every warp of the SM in the same part of the ~45 KB loop
+// Block size of the warp kernel.  One block per SM holding all its resident warps (1024 threads at 64 registers
+// for depths <= 24, 768 at 80 for depths <= 48): the per-tile barrier then keeps every warp of the SM in the same part of the ~45 KB loop
 // body, which exceeds the 32 KB instruction cache (measured +8 % over 128-thread blocks at N = 48, +11 % at
 // N = 12).  The MAD and TMA variants are shared-memory bound and stay at 128 threads.
 template <int NB, bool MAD, bool TMA>
 struct WarpThreads {
     static constexpr int value = MB_WARP_THREADS ? MB_WARP_THREADS
-                                 : ((MAD || TMA) ? 128 : (NB <= 48 ? 768 : (NB <= 64 ? 512 : (NB <= 96 ? 384 : 256))));
+                                 : ((MAD || TMA) ? 128 : (NB <= 24 ? 1024 : (NB <= 48 ? 768 : (NB <= 64 ? 512 : (NB <= 96 ? 384 : 256)))));
 };
 
 // 128-byte opaque image of a CUtensorMap (filled on the host by cuTensorMapEncodeTiled)
@@ -1071,8 +1071,14 @@ namespace mb {
 // of this kernel -- measured: FMNMX 64 lanes/clk/SM, IADD3 more than that, IMAD 64, so the plain
 // FMNMX + IADD3 form sustains ~60 compare-exchanges/clk/SM, twice the 2xIMAD form); per-exposure valid counts come from one 32x32 bit transpose per 32 exposures.
 // ---------------------------------------------------------------------------------------------
+#ifndef MB_MEDIAN_BLOCKS
+#define MB_MEDIAN_BLOCKS 0
+#endif
+// resident 128-thread blocks per SM the median kernel is compiled for: it is bound by memory latency
+// (long_scoreboard leads its stalls), so shallow stacks trade registers for more warps in flight
+template <int NB> struct MedianBlocks { static constexpr int value = MB_MEDIAN_BLOCKS ? MB_MEDIAN_BLOCKS : 1; };
 template <int NB, bool FULL>
-__global__ void __launch_bounds__(kThreads) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A)
+__global__ void __launch_bounds__(kThreads, MedianBlocks<NB>::value) median_warp_kernel(const TileArgs<NB> S, const ClipArgs A)
 {
     constexpr int W = ExpSet<NB>::W;
     const int lane = threadIdx.x & 31;
