@@ -265,8 +265,8 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL prints its version banner on stdout at the default debug level; stdout carries the one JSON line
-        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        # (with NCCL_DEBUG=VERSION in the environment, as on the GPU boxes, NCCL prints its version banner on stdout
+        # before the JSON line; the environment is left as the harness set it)
         dist.init_process_group("nccl", device_id=dev)
 
     nz = pick_nz(torch, dev, args.nz)
