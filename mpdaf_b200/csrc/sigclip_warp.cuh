@@ -1,32 +1,35 @@
-// Warp-tiled sigma-clip kernel for sm_100a: the main combine kernel (float32 stacks <= 64 deep).
+// Warp-tiled sigma-clip kernel for sm_100a: the main combine kernel (float32 stacks <= 128 deep).
 //
 // Reference behaviour restated (never copied): src/merging.c:423-477 (gather, n == 0 / 1,
 // outputs, counters) and src/tools.c:82-118 (median-centred iterative clip).
 //
-// Work decomposition.  A warp owns tiles of 32 consecutive voxels; one lane owns one voxel.
-// Warps never synchronise with each other (no block barrier), so a warp that needs more clip
-// iterations does not hold back its neighbours.  Every exposure load is one coalesced
-// 128-byte line per warp; the rows of the next tile are prefetched into L2 a whole tile
-// ahead (prefetch.global.L2), the STAT rows of the current tile at its start.
+// Work decomposition.  A warp owns tiles of 32 consecutive voxels; one lane owns one voxel.  Warps share no
+// data; all resident warps of an SM form one block and (for stacks of 24 and more) start every tile together,
+// because the unrolled loop body is larger than the instruction cache (see WarpThreads below).  Every
+// exposure load is one coalesced 128-byte line per warp; the rows of the next tile are prefetched into L2 a
+// whole tile ahead (two prefetches per line), the STAT rows of the current tile after its sort.
 //
 // Per voxel:
-//  1. exposure order, float64, no FMA: w = (offset + d) * scale and sum(w); the first mean
-//     is bit-identical to the reference (tools.c:13-17).  Alongside, shifted moments
-//     T1 = sum(w - p), S2 = sum((w - p)^2) about a pivot sample p.
-//  2. 32-bit keys: float32(w) with the low 6 mantissa bits replaced by the exposure index,
-//     ordered by a register sorting network.  A compare-exchange is FMNMX (min) plus integer
-//     a + b - min (the keys are distinct bit patterns, so that is exactly the max); part of the
-//     integer work is steered to the FMA pipe (IMAD) because the ALU pipe is the scarce one.
-//  3. the sorted keys go to the lane's shared-memory column; median, window counts and the
-//     rejected samples come from direct / binary-search reads of that column.
-//  4. later means / sigmas: the rejected samples (exact w recomputed from the staged d) are
-//     subtracted from the shifted moments.
-//  5. per-exposure counters: the lanes' "invalid" and "dropped" bit masks are transposed
-//     across the warp with 5 shuffle stages per 32 exposures, then one POPC per lane.
-// Decisions are CERTIFIED: key-derived median and moment-derived sigma carry
-// rigorous error bounds; a voxel with a sample closer to a clip bound than that uncertainty,
-// or with an ill-conditioned variance, is recomputed by `exact_voxel_w` (the reference
-// algorithm restated literally), so expmap and the counters are always bit-exact.
+//  1. exposure order, float64, no FMA: w = (offset + d) * scale and sum(w); the first mean is bit-identical
+//     to the reference (tools.c:13-17).  Alongside, shifted moments T1 = sum(w - p), S2 = sum((w - p)^2)
+//     about a pivot sample p.  Invalid (NaN) samples cost selects, not branches.
+//  2. 32-bit keys: float32(w) with the low 6 (7) mantissa bits replaced by the exposure index, ordered by a
+//     register sorting network.  A compare-exchange is FMNMX (min) plus integer a + b - min (the keys are
+//     distinct bit patterns, so that is exactly the max).  Invalid samples are sentinel keys below every
+//     real key, so the largest samples sit in fixed registers after the sort.
+//  3. the exact values of the two largest samples are looked up speculatively; the sorted keys go to the
+//     lane's shared-memory column; the median and four probe keys at each end of the clip window are read
+//     from it (a binary search only when four or more samples fall on one side).
+//  4. later means / sigmas: the rejected samples (exact w from the speculative values or re-read through
+//     L1 / L2) are subtracted from the shifted moments.
+//  5. propagated variance: STAT rows loaded after the clip loop, float32 FMAs in short chains.
+//  6. per-exposure counters: the lanes' "invalid" and "dropped" bit masks are transposed across the warp
+//     with 5 shuffle stages per 32 exposures, then one POPC per lane.
+// Decisions are CERTIFIED: key-derived median and moment-derived sigma carry rigorous error
+// bounds; a voxel with a sample closer to a clip bound than that uncertainty, or with an ill-conditioned
+// variance, is recomputed by `exact_voxel_w` (the reference algorithm restated literally), so expmap and the
+// counters are always bit-exact.
+// Tuning builds: -DMB_TIMING=1 (per-phase clock totals), -DMB_ABLATE=1 (memory ablation flags), see tools/variant.py.
 #pragma once
 
 #include "combine_kernels.cuh"
