@@ -503,22 +503,25 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         double sum = 0.0, p = 0.0, T1 = 0.0, S2 = 0.0;
         if constexpr (!TMA) {
             // ---- gather: one coalesced load per exposure ------------------------------------------
+            // STRIDED: idle lanes (ragged last tile, tiles past the end) re-read the last voxel and are voided
+            // after pass 1, so these loads need neither a predicate nor a NaN initialisation per row
+            const long long vc = (STRIDED && !act) ? A.nvox - 1 : v;
 #if MB_ABLATE   // tuning builds: flags & 32 gathers from an L1-resident window (LSU work without L2 / DRAM)
-            const float* rp = (flags & 32) ? S.data[0] + (v & 1023) : S.data[0] + v;
+            const float* rp = (flags & 32) ? S.data[0] + (vc & 1023) : S.data[0] + vc;
             const unsigned gstride = (flags & 32) ? 32u : S.dstride;
 #else
-            const float* rp = S.data[0] + v;
+            const float* rp = S.data[0] + vc;
             const unsigned gstride = S.dstride;
 #endif
 #pragma unroll
             for (int i = 0; i < NB; i++) {
                 // predicated loads: ptxas keeps them batched at the top of the tile (unconditional
                 // ones get sunk next to their first use and their latency serialises)
-                key[i] = CUDART_NAN_F;
                 if constexpr (STRIDED) {
-                    if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(rp));
+                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(rp));
                     asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(rp) : "r"(gstride));
                 } else {
+                    key[i] = CUDART_NAN_F;
                     if (act && i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(S.data[i] + v));
                 }
             }
@@ -579,6 +582,10 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 if (!ok) inval.set(i);
                 const unsigned kb = (__float_as_uint(kf) & keep_mask) | (unsigned)i;
                 key[i] = __uint_as_float(ok ? kb : sentinel);
+            }
+            if (STRIDED && !act) {                         // idle lane: every sample invalid
+#pragma unroll
+                for (int k = 0; k < W; k++) inval.w[k] = (k == W - 1 && (NB & 31)) ? ((1u << (NB & 31)) - 1u) : 0xFFFFFFFFu;
             }
             T1 = T1c[0]; S2 = S2c[0];
 #pragma unroll
