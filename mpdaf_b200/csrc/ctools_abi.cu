@@ -56,9 +56,12 @@ struct DeviceState {
     unsigned long long* counters = nullptr;  // [2][kGenericMax]: valid, select
     StackTable* table = nullptr;             // device copy for the generic kernels
     unsigned long long* slow = nullptr;      // voxels recomputed by the exact fallback (diagnostic)
+    unsigned* slow_q = nullptr;              // queue of voxels the pair kernel hands to the exact kernel
+    unsigned* slow_n = nullptr;
     unsigned long long* hist = nullptr;      // [kGenericMax + 1] exposure-map histogram of the last call
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
+constexpr unsigned kSlowQueueCap = 4u << 20;   // voxels; beyond that the pair kernel recomputes in place
 DeviceState g_dev[16];
 
 int device_ready(int device)
@@ -81,6 +84,8 @@ int device_ready(int device)
     MB_CUDA(cudaMalloc(&d.table, sizeof(StackTable)));
     MB_CUDA(cudaMalloc(&d.slow, sizeof(unsigned long long)));
     MB_CUDA(cudaMemset(d.slow, 0, sizeof(unsigned long long)));
+    MB_CUDA(cudaMalloc(&d.slow_q, (size_t)kSlowQueueCap * sizeof(unsigned)));
+    MB_CUDA(cudaMalloc(&d.slow_n, sizeof(unsigned)));
     MB_CUDA(cudaMalloc(&d.hist, (kGenericMax + 1) * sizeof(unsigned long long)));
     MB_CUDA(cudaEventCreate(&d.ev0));
     MB_CUDA(cudaEventCreate(&d.ev1));
@@ -247,6 +252,9 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         LaunchCtx ctx;
         ctx.sm_count = g_dev[device].sm_count;
         ctx.slow = g_dev[device].slow;
+        ctx.slow_q = j.slow_q ? j.slow_q : g_dev[device].slow_q;     // slab slots bring their own queue (one per stream)
+        ctx.slow_n = j.slow_q ? j.slow_n : g_dev[device].slow_n;
+        ctx.slow_cap = j.slow_q ? j.slow_cap : kSlowQueueCap;
         ctx.stream = stream;
         ctx.name = name;
         ctx.name_len = sizeof name;
@@ -303,6 +311,9 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         LaunchCtx ctx;
         ctx.sm_count = g_dev[device].sm_count;
         ctx.slow = g_dev[device].slow;
+        ctx.slow_q = j.slow_q ? j.slow_q : g_dev[device].slow_q;     // slab slots bring their own queue (one per stream)
+        ctx.slow_n = j.slow_q ? j.slow_n : g_dev[device].slow_n;
+        ctx.slow_cap = j.slow_q ? j.slow_cap : kSlowQueueCap;
         ctx.stream = stream;
         ctx.name = name;
         ctx.name_len = sizeof name;
@@ -346,6 +357,8 @@ struct Slot {
     long long pend_v0 = 0, pend_cnt = 0;   // chunk waiting in h_out for its copy into the caller's buffers
     bool pending = false;
     StackTable* d_table = nullptr;
+    unsigned* slow_q = nullptr;   // this stream's queue of voxels for the exact kernel (sigclip_pair.cuh)
+    unsigned* slow_n = nullptr;
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     bool timed = false;
     size_t in_bytes = 0, chunk_cap = 0, host_bytes = 0;   // current capacities
@@ -354,6 +367,7 @@ struct Slot {
 // The staging slots are kept per device between calls (allocation, pinning and stream creation
 // cost more than a whole small combine); they only ever grow.
 constexpr int kSlots = 3;
+constexpr unsigned kSlotQueueCap = 1u << 20;
 Slot g_slots[16][kSlots];
 
 int ensure_slot(Slot& s, size_t in_bytes, size_t chunk, bool host_staging)
@@ -361,6 +375,8 @@ int ensure_slot(Slot& s, size_t in_bytes, size_t chunk, bool host_staging)
     if (!s.stream) {
         MB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         MB_CUDA(cudaMalloc(&s.d_table, sizeof(StackTable)));
+        MB_CUDA(cudaMalloc(&s.slow_q, (size_t)kSlotQueueCap * sizeof(unsigned)));
+        MB_CUDA(cudaMalloc(&s.slow_n, sizeof(unsigned)));
         MB_CUDA(cudaEventCreate(&s.k0));
         MB_CUDA(cudaEventCreate(&s.k1));
     }
@@ -575,6 +591,9 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         j.data = dptr.data();
         j.var = need_var ? dptr.data() + nfiles : nullptr;
         j.table_dev = s.d_table;
+        j.slow_q = s.slow_q;
+        j.slow_n = s.slow_n;
+        j.slow_cap = kSlotQueueCap;
         j.a.nvox = cnt;
         j.a.out = s.d_out;
         j.a.outvar = s.d_var;

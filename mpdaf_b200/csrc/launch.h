@@ -20,6 +20,9 @@ struct Job {
     const double* scale = nullptr;       // host, may be null
     const double* offset = nullptr;
     StackTable* table_dev = nullptr;     // device scratch for the generic kernels' stack table
+    unsigned* slow_q = nullptr;          // per-stream queue for the pair kernel's exact pass (null: the device's own)
+    unsigned* slow_n = nullptr;
+    unsigned slow_cap = 0;
     ClipArgs a{};
 };
 
@@ -27,6 +30,9 @@ struct Job {
 struct LaunchCtx {
     int sm_count = 0;
     unsigned long long* slow = nullptr;  // device counter of exact-fallback voxels
+    unsigned* slow_q = nullptr;          // device queue of voxels the pair kernel could not certify
+    unsigned* slow_n = nullptr;          // its fill count
+    unsigned slow_cap = 0;
     cudaStream_t stream = nullptr;
     char* name = nullptr;                // receives the kernel family name
     size_t name_len = 0;

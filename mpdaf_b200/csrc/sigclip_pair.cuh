@@ -1,0 +1,794 @@
+// Pair-packed, TMA-pipelined sigma-clip kernel for sm_100a: the main combine kernel of round 2
+// (float32 stacks up to 64 deep whose rows are equally pitched and 16-byte aligned).
+//
+// Reference behaviour restated (never copied): src/merging.c:423-477 (gather, n == 0 / 1, outputs,
+// counters) and src/tools.c:82-118 (median-centred iterative clip, strict window, stop rules).
+//
+// Why a new formulation.  The round-1 warp kernel (sigclip_warp.cuh) is bound by the 16-lane ALU pipe: a
+// compare-exchange on 32-bit keys costs two ALU-pipe instructions per voxel, its exposure rows are gathered
+// into registers by the computing warps themselves, and its 45 KB loop body forces all warps of an SM into the
+// same phase.  Here
+//  * a lane owns TWO neighbouring voxels and their 16-bit keys share a register, so one HMNMX2.BF16 min plus
+//    one max performs the compare-exchange of both voxels: half the sort instructions per voxel;
+//  * the keys are bfloat16(w - pivot) with no exposure index.  Which exposures fall outside the clip window is
+//    recovered afterwards by ONE packed comparison pass (2 HSETP2 per exposure for both voxels) of the unsorted
+//    keys, kept in registers, against the window's boundary keys -- and only when something is rejected;
+//  * a producer warp streams [NB][64] tiles into a ring of shared-memory stages with cp.async.bulk.tensor
+//    (TMA, mbarrier completion); consumer warps never wait on a load they issued themselves, and the STAT tile
+//    of a voxel pair lands in the stage its DATA tile occupied, while the sort and the clip loop run;
+//  * dropped samples (invalid or rejected) are zeroed in the staged STAT tile, so the propagated variance is an
+//    unpredicated FFMA stream; pass 1 is predicated PTX (one FSETP per sample, no selects, no branches).
+// Decisions stay CERTIFIED: a key differs from its sample's w - pivot by at most KREL * |key| + E0, an order
+// statistic of the keys from the same order statistic of the samples by the same bound (both maps are
+// monotone), and sigma comes from float64 shifted moments (2^-28 relative, conditioning checked).  A voxel is
+// classified from its keys only if no key lies within that uncertainty of a clip bound; every other voxel goes
+// to a queue and is recomputed by the reference algorithm restated literally (sigclip_pair_slow_kernel: one
+// thread per queued voxel, full warps instead of one slow lane stalling 63 fast ones).  expmap and the
+// per-exposure counters are therefore bit-exact, means and variances within ~1e-15 / 3e-7 relative.
+#pragma once
+
+#include "sigclip_warp.cuh"
+
+#ifndef MB_PAIR_LOOKAHEAD
+#define MB_PAIR_LOOKAHEAD 0   // 0: as many free stages as shared memory allows (at least 2, at most 8)
+#endif
+#ifndef MB_PAIR_CONSUMERS
+#define MB_PAIR_CONSUMERS 0   // 0: per-depth default (PairCfg)
+#endif
+
+namespace mb {
+
+template <int NB>
+struct PairArgs {
+    const float* data0;                    // row 0 of the DATA stack
+    const float* var0;                     // row 0 of the STAT stack (null unless var = 'propagate')
+    unsigned long long dstride, vstride;   // elements between consecutive rows
+    double2 os[NB];                        // (offset, scale)
+    double osp[NB];                        // offset * scale
+    float kscale[NB];                      // float32(scale)
+    float koffset[NB];                     // float32(offset * scale)
+    float scale2f[NB];                     // float32(scale^2)
+    double scale2[NB];
+    double osmax;                          // max |offset * scale|: part of the absolute key error
+};
+
+template <int NB>
+struct PairCfg {
+    static constexpr int stage_bytes = NB * 64 * 4;    // one [NB][64] float32 tile
+    static constexpr int col_bytes = NB * 32 * 4;      // sorted packed keys of one warp
+    static constexpr int misc_bytes = 4096;            // barriers, reciprocal table, per-exposure constants
+    static constexpr int budget = 227 * 1024 - misc_bytes;
+    // consumer warps: bounded by the register file (about 2 NB + 72 registers per thread: sorted and unsorted packed
+    // keys plus the per-voxel state), by 15 (four warps per scheduler with the producer), and by shared memory
+    static constexpr int c_regs = 2048 / (2 * NB + 72) - 1;
+    static constexpr int c_smem = (budget - 2 * stage_bytes) / (stage_bytes + col_bytes);
+    static constexpr int c_auto = c_regs < 15 ? (c_regs < c_smem ? c_regs : c_smem) : (15 < c_smem ? 15 : c_smem);
+    static constexpr int C = MB_PAIR_CONSUMERS ? MB_PAIR_CONSUMERS : c_auto;
+    // ring stages: a stage is held from the TMA request to the end of its consumer's pass 1; C of them are in
+    // use at the start of a phase-locked round, the rest is lookahead
+    static constexpr int st_fit = (budget - C * col_bytes) / stage_bytes;
+    static constexpr int ST = MB_PAIR_LOOKAHEAD ? C + MB_PAIR_LOOKAHEAD : (st_fit > C + 4 ? C + 4 : st_fit);
+    static constexpr int threads = (C + 1) * 32;       // consumers + one producer warp
+    static_assert(C >= 2 && ST >= C, "stack too deep for the pair kernel");
+};
+
+template <int NB>
+struct PairSmem {
+    float stage[PairCfg<NB>::ST][NB][64];                 // DATA tiles
+    unsigned col[PairCfg<NB>::C][NB][32];                 // sorted keys: low half voxel 2l, high half voxel 2l+1
+    double rcp[NB + 1];
+    double2 os[NB];                                       // (offset, scale) for lane-dependent lookups
+    float2 kso[NB];                                       // float32 (scale, offset * scale), likewise
+    unsigned long long full[PairCfg<NB>::ST];             // TMA completion of a stage's DATA tile
+    unsigned long long empty[PairCfg<NB>::ST];            // consumer has finished with the stage
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// producer-side wait: the thread may be suspended up to the hint (ns) per try instead of spinning on the issue port
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar_addr, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITR_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONER_%=;\n\t"
+        "bra WAITR_%=;\n\t"
+        "DONER_%=:\n\t}" ::"r"(bar_addr), "r"(parity), "r"(20000u) : "memory");
+}
+
+// key error model: bfloat16 rounding of t32 (2^-8 relative) + float32 evaluation of w - pivot
+constexpr double kPairKrel = 0x1.1p-8;
+constexpr double kPairC1 = (1.0 / (1.0 + kPairKrel)) * (1.0 - 0x1p-40);   // <= 1 / (1 + KREL)
+constexpr double kPairC2 = (1.0 / (1.0 - kPairKrel)) * (1.0 + 0x1p-40);   // >= 1 / (1 - KREL)
+constexpr unsigned kPairSent = 0xFF7F0000u;   // float32 image of the most negative finite bfloat16: key of an invalid sample
+
+// The reference algorithm restated literally for one voxel of a strided stack; stores the outputs and corrects
+// the per-exposure `selected` counters (the main kernel counted every valid sample of a queued voxel as kept).
+template <int NB, bool UNIT>
+__device__ __noinline__ void exact_voxel_store(const PairArgs<NB>& S, const ClipArgs& A, long long v)
+{
+    GenericScratch<NB> g;
+    const int nfiles = A.nfiles;
+    int n = 0;
+    for (int i = 0; i < nfiles; i++) {
+        const float x = __ldg(S.data0 + (size_t)i * S.dstride + v);
+        if (x == x) {
+            g.w[n] = UNIT ? (double)x : (S.os[i].x + (double)x) * S.os[i].y;
+            g.file[n] = (unsigned short)i;
+            g.idx[n] = (unsigned short)n;
+            n++;
+        }
+    }
+    double mean = CUDART_NAN, sigma = 0.0, ov = CUDART_NAN;
+    int kept = n;
+    if (n == 1) mean = g.w[0];
+    if (n >= 2) kept = clip_generic<NB>(g, n, A.nmax, A.nclip_low, A.nclip_up, A.nstop < 1 ? 1 : A.nstop, 0, mean, sigma);
+    if (n >= 1) {
+        if (A.typ_var == 0) {
+            double vs = 0.0;
+            for (int k = 0; k < kept; k++) {                                       // merging.c:461-462
+                const int i = g.file[g.idx[k]];
+                vs += (double)__ldg(S.var0 + (size_t)i * S.vstride + v) * S.scale2[i];
+            }
+            ov = vs / ((double)kept * (double)kept);
+        } else if (kept > 1) {
+            ov = sigma * sigma;                                                    // merging.c:465
+            if (A.typ_var == 1) ov /= (double)(kept - 1);                          // merging.c:467
+        }
+    }
+    if (n >= 2 && kept < n) {
+        // rejected = valid but not among the survivors g.idx[0 .. kept)
+        unsigned keep[(NB + 31) / 32];
+        for (int k = 0; k < (NB + 31) / 32; k++) keep[k] = 0u;
+        for (int k = 0; k < kept; k++) {
+            const int i = g.file[g.idx[k]];
+            keep[i >> 5] |= 1u << (i & 31);
+        }
+        for (int k = 0; k < n; k++) {
+            const int i = g.file[k];
+            if (!((keep[i >> 5] >> (i & 31)) & 1u)) atomicAdd(A.select_cnt + i, ~0ull);   // -1
+        }
+    }
+    A.out[v] = mean;
+    A.outvar[v] = ov;
+    A.expmap[v] = kept;
+}
+
+// Queued voxels: the reference algorithm restated literally (merging.c:423-477, tools.c:9-24, :39-51, :82-118), one
+// WARP per voxel.  The samples (<= 64: two per lane) are compacted in file order into shared memory, ranked
+// against each other (ties by position, so the ranks are a permutation) and scattered into an ascending copy; the
+// sums the decisions depend on run sequentially in the reference's order (file order first, ascending afterwards)
+// and redundantly in every lane, the strict window counts are ballots.  Survivors of a clip are a contiguous range
+// of the ascending copy (verified restatement).  Also corrects the per-exposure `selected` counters:
+// the main kernel counted every valid sample of a queued voxel as kept.
+template <int NB, bool UNIT>
+__global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<NB> S, const ClipArgs A, const unsigned* __restrict__ queue,
+                                                                const unsigned* __restrict__ count, unsigned cap,
+                                                                unsigned long long* slow_total)
+{
+    __shared__ double s_w[4][64];            // valid samples in file order (later: the kept samples' variances)
+    __shared__ double s_s[4][64];            // ascending
+    __shared__ unsigned char s_f[4][64];     // exposure of the ascending samples
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const unsigned nq = min(*count, cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && slow_total != nullptr) atomicAdd(slow_total, (unsigned long long)*count);
+    const int nfiles = A.nfiles;
+    const int nstop = A.nstop < 1 ? 1 : A.nstop;
+    const unsigned lt = (1u << lane) - 1u;
+    double* fw = s_w[wp];
+    double* sw = s_s[wp];
+    unsigned char* sf = s_f[wp];
+    for (unsigned q = blockIdx.x * 4 + wp; q < nq; q += gridDim.x * 4) {
+        const long long v = (long long)queue[q];
+        double w[2];
+        bool ok[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const int i = lane + 32 * s;
+            const float x = i < nfiles ? __ldg(S.data0 + (size_t)i * S.dstride + v) : CUDART_NAN_F;
+            ok[s] = (x == x);
+            const double2 os = S.os[i < NB ? i : 0];
+            w[s] = UNIT ? (double)x : (os.x + (double)x) * os.y;                 // merging.c:426
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
+        const int n0 = __popc(b0), n = n0 + __popc(b1);
+        const int pos[2] = {__popc(b0 & lt), n0 + __popc(b1 & lt)};
+        __syncwarp();
+        if (ok[0]) fw[pos[0]] = w[0];
+        if (ok[1]) fw[pos[1]] = w[1];
+        __syncwarp();
+        double mean = CUDART_NAN, sigma = 0.0;
+        int a = 0, b = n;
+        if (n == 1) mean = fw[0];
+        if (n >= 2) {
+            // ascending copy by ranking (equal values keep their file order: any order of equal values gives the same sums)
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                if (!ok[s]) continue;
+                int r = 0;
+                for (int j = 0; j < n; j++) {
+                    const double wj = fw[j];
+                    r += (wj < w[s] || (wj == w[s] && j < pos[s])) ? 1 : 0;
+                }
+                sw[r] = w[s];
+                sf[r] = (unsigned char)(lane + 32 * s);
+            }
+            __syncwarp();
+            // first statistics in file order (tools.c:13-22)
+            double acc = 0.0;
+            for (int j = 0; j < n; j++) acc += fw[j];
+            mean = acc / n;
+            double dev = 0.0;
+            for (int j = 0; j < n; j++) dev += (fw[j] - mean) * (fw[j] - mean);
+            sigma = sqrt(dev / n);
+            int it = A.nmax;
+            for (;;) {
+                const int m = b - a;
+                const double med = (m & 1) ? sw[a + (m >> 1)] : (sw[a + (m >> 1)] + sw[a + (m >> 1) - 1]) / 2;   // tools.c:45-48
+                const double clo = med - (A.nclip_low * sigma);
+                const double cup = med + (A.nclip_up * sigma);
+                int ni = 0, nle = 0;
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const int j = a + lane + 32 * s;
+                    const double x = j < b ? sw[j] : 0.0;
+                    const bool gt = (j < b) && (x > clo), in = gt && (x < cup);      // strict window, tools.c:95
+                    ni += __popc(__ballot_sync(0xffffffffu, in));
+                    nle += __popc(__ballot_sync(0xffffffffu, (j < b) && !gt));
+                }
+                if (ni < nstop || ni == m) break;                                      // tools.c:100-103
+                if (it <= 0) break;                                                    // tools.c:104
+                it--;
+                a += nle;
+                b = a + ni;
+                acc = 0.0;                                                             // survivors, ascending order (tools.c:116 -> :13-22)
+                for (int j = a; j < b; j++) acc += sw[j];
+                mean = acc / ni;
+                dev = 0.0;
+                for (int j = a; j < b; j++) dev += (sw[j] - mean) * (sw[j] - mean);
+                sigma = sqrt(dev / ni);
+            }
+        }
+        const int kept = b - a;
+        double ov = CUDART_NAN;
+        if (n >= 1) {
+            if (A.typ_var == 0) {
+                // variances of the kept samples in the order of their values (merging.c:461-462)
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                    const int j = a + lane + 32 * s;
+                    if (j < b) {
+                        const int i = n >= 2 ? (int)sf[j] : (b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1);
+                        fw[j - a] = (double)__ldg(S.var0 + (size_t)i * S.vstride + v) * S.scale2[i];
+                    }
+                }
+                __syncwarp();
+                double vs = 0.0;
+                for (int j = 0; j < kept; j++) vs += fw[j];
+                ov = vs / ((double)kept * (double)kept);
+            } else if (kept > 1) {
+                ov = sigma * sigma;                                                    // merging.c:465
+                if (A.typ_var == 1) ov /= (double)(kept - 1);                          // merging.c:467
+            }
+        }
+        if (n >= 2) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int j = lane + 32 * s;
+                if (j < n && (j < a || j >= b)) atomicAdd(A.select_cnt + sf[j], ~0ull);   // -1: valid but rejected
+            }
+        }
+        if (lane == 0) {
+            A.out[v] = mean;
+            A.outvar[v] = ov;
+            A.expmap[v] = kept;
+        }
+        __syncwarp();
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void sort_pairs(unsigned (&a)[NB])
+{
+#define MB_CE(i, j)                                                             \
+    {                                                                           \
+        unsigned lo_, hi_;                                                      \
+        asm("min.bf16x2 %0, %1, %2;" : "=r"(lo_) : "r"(a[i]), "r"(a[j]));       \
+        asm("max.bf16x2 %0, %1, %2;" : "=r"(hi_) : "r"(a[i]), "r"(a[j]));       \
+        a[i] = lo_;                                                             \
+        a[j] = hi_;                                                             \
+    }
+    if constexpr (NB == 4) { MB_SORTNET_4(MB_CE) }
+    else if constexpr (NB == 8) { MB_SORTNET_8(MB_CE) }
+    else if constexpr (NB == 12) { MB_SORTNET_12(MB_CE) }
+    else if constexpr (NB == 16) { MB_SORTNET_16(MB_CE) }
+    else if constexpr (NB == 24) { MB_SORTNET_24(MB_CE) }
+    else if constexpr (NB == 32) { MB_SORTNET_32(MB_CE) }
+    else if constexpr (NB == 48) { MB_SORTNET_48(MB_CE) }
+    else if constexpr (NB == 64) { MB_SORTNET_64(MB_CE) }
+#undef MB_CE
+}
+
+// Grid: one block per SM (persistent).  Block: PairCfg<NB>::C consumer warps + 1 producer warp.
+// Tiles of 64 consecutive voxels; block b takes tiles b, b + grid, b + 2 grid, ...; its k-th tile uses
+// ring stage k % ST and is processed by consumer warp k % C.  flags & 1: the consumer warps start every
+// round of C tiles together (named barrier), so that a line of the long straight-line loop body is fetched
+// once per SM and round instead of once per warp.
+template <int NB, bool UNIT, bool PROP>
+__global__ void __launch_bounds__(PairCfg<NB>::threads, 1)
+sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntiles, unsigned* __restrict__ slow_q,
+                    unsigned* __restrict__ slow_n, const unsigned slow_cap, const int flags, const __grid_constant__ TmaMaps M)
+{
+    using Cfg = PairCfg<NB>;
+    constexpr int C = Cfg::C, ST = Cfg::ST;
+    constexpr int W = ExpSet<NB>::W;
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr unsigned kTileBytes = NB * 64 * sizeof(float);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    PairSmem<NB>& sm = *reinterpret_cast<PairSmem<NB>*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int nstop = A.nstop < 1 ? 1 : A.nstop;
+
+    for (int i = tid; i <= NB; i += Cfg::threads) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
+    for (int i = tid; i < NB; i += Cfg::threads) {
+        sm.os[i] = S.os[i];
+        sm.kso[i] = make_float2(S.kscale[i], S.koffset[i]);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < ST; s++) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();   // the only block-wide barrier
+
+    // ---- producer warp: one lane keeps the ring full -------------------------------------------------
+    if (warp == C) {
+        if (lane == 0) {
+            long long tile = blockIdx.x;
+            for (unsigned k = 0; tile < ntiles; k++, tile += gridDim.x) {
+                const unsigned st = k % ST, ph = (k / ST) & 1u;
+                mbar_wait_relaxed(smem_u32(&sm.empty[0]) + 8u * st, ph ^ 1u);   // a fresh barrier passes the wait on parity 1
+                mbar_expect_tx(&sm.full[st], kTileBytes);
+                tma_load_2d(&sm.stage[st][0][0], &M.data, (int)(tile << 6), 0, &sm.full[st]);
+            }
+        }
+        return;
+    }
+
+    // ---- consumer warps -------------------------------------------------------------------------------
+    const int c = warp;
+    TransposeConsts tc;
+    tc.init(lane);
+    unsigned cnt_inval[W], cnt_drop[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) { cnt_inval[k] = 0u; cnt_drop[k] = 0u; }
+    unsigned tiles_done = 0;
+    const unsigned short* colh = reinterpret_cast<const unsigned short*>(&sm.col[c][0][lane]);   // key q of voxel h: colh[q * 64 + h]
+    auto col16 = [&](int q, int h) -> unsigned { return (unsigned)colh[q * 64 + h]; };
+    auto keyf = [&](int q, int h) -> float { return __uint_as_float(col16(q, h) << 16); };
+    const float nlo32 = (float)A.nclip_low, nup32 = (float)A.nclip_up;
+    // float32 images of the clip factors must not be smaller than the factors (conservative bounds need |error| only)
+    const float krel32 = (float)kPairKrel, c1f = (float)(kPairC1 * (1.0 - 0x1p-20)), c2f = (float)(kPairC2 * (1.0 + 0x1p-20));
+
+    // rounds of C tiles; the trip count is uniform over the consumer warps so that the round barrier is legal
+    const long long my_tiles = ntiles > (long long)blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long rounds = (my_tiles + C - 1) / C;
+    for (long long r = 0; r < rounds; r++) {
+        if (flags & 1) asm volatile("bar.sync 1, %0;" ::"n"(C * 32) : "memory");
+        const long long kk64 = r * C + c;
+        if (kk64 >= my_tiles) continue;
+        const unsigned k = (unsigned)kk64;
+        const long long tile = (long long)blockIdx.x + kk64 * gridDim.x;
+        const unsigned st = k % ST, ph = (k / ST) & 1u;
+        float (*dt)[64] = sm.stage[st];
+        const long long v0 = (tile << 6) + 2 * lane;            // this lane's voxels: v0, v0 + 1
+        // the STAT tile of these voxels is wanted at the end of the tile: start it on its way into L2 now
+        if (PROP && lane == 0) tma_prefetch_2d(&M.stat, (int)(tile << 6), 0);
+        mbar_wait(&sm.full[st], ph);
+
+        // ---- pivot: median of the first three samples (robust against one outlier), else the fourth, else 0
+        float pf[2];
+        {
+            const float2 r0 = *reinterpret_cast<const float2*>(&dt[0][2 * lane]);
+            const float2 r1 = *reinterpret_cast<const float2*>(&dt[1][2 * lane]);
+            const float2 r2 = *reinterpret_cast<const float2*>(&dt[2][2 * lane]);
+            const float2 r3 = *reinterpret_cast<const float2*>(&dt[3][2 * lane]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                float x0 = h ? r0.y : r0.x, x1 = h ? r1.y : r1.x, x2 = h ? r2.y : r2.x, x3 = h ? r3.y : r3.x;
+                if constexpr (!UNIT) {
+                    x0 = __fmaf_rn(x0, S.kscale[0], S.koffset[0]);
+                    x1 = __fmaf_rn(x1, S.kscale[1], S.koffset[1]);
+                    x2 = __fmaf_rn(x2, S.kscale[2], S.koffset[2]);
+                    x3 = __fmaf_rn(x3, S.kscale[3], S.koffset[3]);
+                }
+                float m3 = fmaxf(fminf(x0, x1), fminf(fmaxf(x0, x1), x2));   // fminf / fmaxf skip NaNs
+                m3 = (m3 == m3) ? m3 : x3;
+                m3 = (m3 == m3 && fabsf(m3) < 0x1p100f) ? m3 : 0.f;
+                pf[h] = m3;
+            }
+        }
+        const double p[2] = {(double)pf[0], (double)pf[1]};
+
+        // ---- pass 1: exposure order; float64 shifted moments, float32 key values, invalid masks ------------
+        // Per voxel and exposure: one conversion, t = w - pivot as ONE fused multiply-add on (offset * scale - pivot)
+        // [w itself is never needed: |t - (w_ref - pivot)| <= 2^-52 (|w| + |pivot|), far inside the margin of the
+        // bounds], two moment updates, and the float32 key value.  Per voxel PAIR: one conversion to packed
+        // bfloat16, one NaN test giving both voxels' "invalid" predicates, one packed max that turns NaN keys into
+        // the sentinel; an invalid sample's t gets its high word cleared (a denormal: the unconditional moment
+        // updates absorb it without a trace), its mask bit is added under the predicate.
+        unsigned key[NB], ukey[NB];
+        ExpSet<NB> inval[2];
+        double T1[2] = {0.0, 0.0}, S2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const float2 dd = *reinterpret_cast<const float2*>(&dt[i][2 * lane]);
+            double t[2];
+            float tf[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const float d = h ? dd.y : dd.x;
+                if constexpr (UNIT) {
+                    t[h] = (double)d - p[h];
+                    tf[h] = d - pf[h];
+                } else {
+                    t[h] = __fma_rn((double)d, S.os[i].y, S.osp[i] - p[h]);      // (offset + d) * scale - pivot, merging.c:426
+                    tf[h] = __fmaf_rn(d, S.kscale[i], S.koffset[i]) - pf[h];
+                }
+            }
+            asm("{\n\t.reg .pred q0, q1;\n\t.reg .b32 lo0, hi0, lo1, hi1;\n\t"
+                "cvt.rn.bf16x2.f32 %0, %7, %6;\n\t"                 // high half <- voxel 1
+                "setp.nan.bf16x2 q0|q1, %0, %0;\n\t"
+                "max.bf16x2 %1, %0, %8;\n\t"                        // NaN halves -> sentinel key
+                "mov.b64 {lo0, hi0}, %2;\n\t"
+                "mov.b64 {lo1, hi1}, %3;\n\t"
+                "selp.b32 hi0, 0, hi0, q0;\n\t"
+                "selp.b32 hi1, 0, hi1, q1;\n\t"
+                "mov.b64 %2, {lo0, hi0};\n\t"
+                "mov.b64 %3, {lo1, hi1};\n\t"
+                "@q0 add.u32 %4, %4, %9;\n\t"
+                "@q1 add.u32 %5, %5, %9;\n\t}"
+                : "=r"(ukey[i]), "=r"(key[i]), "+d"(t[0]), "+d"(t[1]), "+r"(inval[0].w[i >> 5]), "+r"(inval[1].w[i >> 5])
+                : "f"(tf[0]), "f"(tf[1]), "r"(0xFF7FFF7Fu), "r"(1u << (i & 31)));
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                T1[h] += t[h];
+                S2[h] = __fma_rn(t[h], t[h], S2[h]);
+            }
+        }
+        // ---- the samples are consumed: hand the stage back to the producer --------------------------------------
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
+
+        int n[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            n[h] = NB - inval[h].count();
+            // what the cleared-high-word denormals of invalid samples may have left behind when every real term is 0
+            if (fabs(T1[h]) < 0x1p-1000) T1[h] = 0.0;
+        }
+
+        // ---- order the packed keys; sorted column to shared memory ------------------------------------------
+        sort_pairs<NB>(key);
+#pragma unroll
+        for (int q = 0; q < NB; q++) sm.col[c][q][lane] = key[q];
+        __syncwarp();
+
+        // ---- clip iterations (tools.c:82-118), both voxels in lockstep ---------------------------------------
+        // The variance comes from the float64 moments; everything that only feeds DECISIONS (sigma, bounds, key-space
+        // thresholds) is float32 arithmetic whose rounding is covered by the 2^-19 relative term of the margin.
+        int a[2], b[2], itl[2];
+        bool done[2], slow[2];
+        double varl[2] = {0.0, 0.0}, S2_0[2];
+        float e0[2];
+        ExpSet<NB> rej[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            a[h] = NB - n[h];
+            b[h] = NB;
+            itl[h] = A.nmax;
+            S2_0[h] = S2[h];
+            slow[h] = false;
+            // S2 == 0: every valid sample equals the pivot, sigma == 0, nothing lies strictly inside the empty
+            // window: the reference stops at once with all samples kept (tools.c:100)
+            done[h] = (n[h] < 2) || (S2[h] == 0.0);
+            if (n[h] >= 2 && !(S2[h] < 0x1p200)) { slow[h] = true; done[h] = true; }   // non-finite or absurd values
+            e0[h] = 0x1p-21f * (fabsf(pf[h]) + (float)S.osmax) + 0x1p-100f;
+        }
+        for (;;) {
+            if (!__any_sync(FULLM, !(done[0] && done[1]))) break;
+            unsigned thr_lo = 0xFF80FF80u, thr_hi = 0x7F807F80u;   // (-inf, -inf), (+inf, +inf): match nothing
+            int ncl[2] = {0, 0}, nch[2] = {0, 0};                  // candidates for rejection at the low / high end
+            float clo32[2] = {0.f, 0.f}, cup32[2] = {0.f, 0.f}, tb32[2] = {0.f, 0.f};
+            // ---- part A: sigma, bounds, and the keys that are not CERTAINLY inside the window -------------------
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (done[h]) continue;
+                const int m = b[h] - a[h];
+                const double rm = sm.rcp[m];
+                const double dm1 = T1[h] * rm;
+                const double var_k = __fma_rn(S2[h], rm, -(dm1 * dm1));
+                // conditioning: the moment variance must dominate its rounding error; and it must sit in float32 range
+                if (!(var_k >= 0x1p-13 * (S2_0[h] * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100)) { slow[h] = done[h] = true; continue; }
+                varl[h] = var_k;
+                if (itl[h] <= 0) { done[h] = true; continue; }                       // tools.c:104: no clip left, these statistics stand
+                float sg;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(__double2float_rn(var_k)));   // 2^-21 relative in all
+                const int ih = a[h] + (m >> 1);
+                const int il = ih - 1 + (m & 1);
+                const float kh = keyf(ih, h), kl = keyf(il, h);
+                const float km = 0.5f * (kh + kl);                                   // median of the keys (tools.c:45-48)
+                const float lo_s = nlo32 * sg, up_s = nup32 * sg;
+                const float clo = km - lo_s, cup = km + up_s;
+                // uncertainty of a bound: key median (KREL |key| + e0), sigma, float32 roundings of this very arithmetic
+                const float Tb = krel32 * fmaxf(fabsf(kh), fabsf(kl)) + e0[h] + 0x1p-19f * (fabsf(km) + lo_s + up_s);
+                if (!(Tb < 0x1p100f)) { slow[h] = done[h] = true; continue; }        // NaN / inf bounds
+                // a key in (kL2, kU2) belongs to a sample that is certainly inside the window
+                const float yl = clo + Tb + e0[h], xu = cup - Tb - e0[h];
+                const float kL2 = yl * (yl >= 0.f ? c2f : c1f);
+                const float kU2 = xu * (xu >= 0.f ? c1f : c2f);
+                float kl4[5], ku4[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    const int ql = a[h] + j, qu = b[h] - 1 - j;
+                    kl4[j] = ql < b[h] ? keyf(ql < NB ? ql : NB - 1, h) : CUDART_INF_F;
+                    ku4[j] = qu >= a[h] ? keyf(qu >= 0 ? qu : 0, h) : -CUDART_INF_F;
+                }
+                int jl = 0, ju = 0;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    jl += (jl == j && !(kl4[j] > kL2)) ? 1 : 0;
+                    ju += (ju == j && !(ku4[j] < kU2)) ? 1 : 0;
+                }
+                // at most four candidates per side (the probes' reach), and the two ends must not meet
+                if (jl > 4 || ju > 4 || jl + ju > m) { slow[h] = done[h] = true; continue; }
+                if (jl + ju == 0) { done[h] = true; continue; }                     // everything inside: tools.c:100
+                ncl[h] = jl;
+                nch[h] = ju;
+                clo32[h] = clo;
+                cup32[h] = cup;
+                tb32[h] = Tb;
+                // boundary keys: the candidates are the window's keys at or below BL / at or above BU
+                const unsigned BL = jl > 0 ? col16(a[h] + jl - 1, h) : 0xFF80u;
+                const unsigned BU = ju > 0 ? col16(b[h] - ju, h) : 0x7F80u;
+                if (h == 0) {
+                    thr_lo = (thr_lo & 0xFFFF0000u) | BL;
+                    thr_hi = (thr_hi & 0xFFFF0000u) | BU;
+                } else {
+                    thr_lo = (thr_lo & 0x0000FFFFu) | (BL << 16);
+                    thr_hi = (thr_hi & 0x0000FFFFu) | (BU << 16);
+                }
+            }
+            if (!__any_sync(FULLM, (ncl[0] | nch[0] | ncl[1] | nch[1]) != 0)) continue;
+            // ---- which exposures are those?  one packed comparison pass over the unsorted keys -------------------
+            // (invalid samples are NaN in the unsorted keys and match nothing; the bits of a mask word are distinct, so
+            // they are ADDED under the predicates: predicated integer adds are full rate, LOP3 is not)
+            unsigned RL[2][W], RH[2][W];
+#pragma unroll
+            for (int kk = 0; kk < W; kk++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    asm volatile("mov.b32 %0, 0;" : "=r"(RL[h][kk]));
+                    asm volatile("mov.b32 %0, 0;" : "=r"(RH[h][kk]));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                    "setp.le.bf16x2 p0|p1, %4, %5;\n\t"
+                    "setp.ge.bf16x2 p2|p3, %4, %6;\n\t"
+                    "@p0 add.u32 %0, %0, %7;\n\t"
+                    "@p1 add.u32 %1, %1, %7;\n\t"
+                    "@p2 add.u32 %2, %2, %7;\n\t"
+                    "@p3 add.u32 %3, %3, %7;\n\t}"
+                    : "+r"(RL[0][i >> 5]), "+r"(RL[1][i >> 5]), "+r"(RH[0][i >> 5]), "+r"(RH[1][i >> 5])
+                    : "r"(ukey[i]), "r"(thr_lo), "r"(thr_hi), "r"(1u << (i & 31)));
+            }
+            // ---- part B: the candidates' exact values decide (re-read through L2; the first one of each voxel at once) -----
+            int first[2] = {-1, -1};
+            float dfirst[2] = {0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                int cl = 0, ch = 0;
+#pragma unroll
+                for (int kk = 0; kk < W; kk++) {
+                    RL[h][kk] &= ~rej[h].w[kk];      // samples rejected earlier lie beyond the window
+                    RH[h][kk] &= ~rej[h].w[kk];
+                    cl += __popc(RL[h][kk]);
+                    ch += __popc(RH[h][kk]);
+                }
+                if ((ncl[h] | nch[h]) != 0 && (cl != ncl[h] || ch != nch[h])) {   // key ties the model does not cover
+                    slow[h] = done[h] = true;
+                    ncl[h] = nch[h] = 0;
+                }
+                if ((ncl[h] | nch[h]) == 0) continue;
+#pragma unroll
+                for (int kk = W - 1; kk >= 0; kk--)
+                    if (RL[h][kk] | RH[h][kk]) first[h] = 32 * kk + (__ffs(RL[h][kk] | RH[h][kk]) - 1);
+                dfirst[h] = __ldg(S.data0 + (size_t)first[h] * S.dstride + (v0 + h));
+            }
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if ((ncl[h] | nch[h]) == 0) continue;
+                const double clo_d = (double)clo32[h], cup_d = (double)cup32[h], tb_d = (double)tb32[h];
+                double dT1 = 0.0, dS2 = 0.0;
+                int rl = 0, rh = 0;
+                bool unc = false;
+                float kmax_rl = -CUDART_INF_F, kmin_kl = CUDART_INF_F, kmin_rh = CUDART_INF_F, kmax_kh = -CUDART_INF_F;
+                ExpSet<NB> nr;
+#pragma unroll
+                for (int kk = 0; kk < W; kk++) {
+                    unsigned mw = RL[h][kk] | RH[h][kk];
+                    while (mw) {
+                        const int i = 32 * kk + (__ffs(mw) - 1);
+                        mw &= mw - 1u;
+                        const bool low = (RL[h][kk] >> (i & 31)) & 1u;
+                        const float dval = (i == first[h]) ? dfirst[h] : __ldg(S.data0 + (size_t)i * S.dstride + (v0 + h));
+                        const double2 osj = sm.os[i];
+                        const float2 ksj = sm.kso[i];
+                        const double t = UNIT ? (double)dval - p[h] : __fma_rn((double)dval, osj.y, osj.x * osj.y - p[h]);
+                        const float t32 = UNIT ? dval - pf[h] : __fmaf_rn(dval, ksj.x, ksj.y) - pf[h];
+                        unsigned kb;
+                        asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(kb) : "f"(t32));
+                        const float tk = __uint_as_float(kb & 0xFFFF0000u);          // this sample's key, as in pass 1
+                        const double diff = t - (low ? clo_d : cup_d);
+                        unc = unc || !(fabs(diff) > tb_d);
+                        const bool out = low ? (diff <= 0.0) : (diff >= 0.0);        // strict window, tools.c:95
+                        if (out) {
+                            dT1 += t;
+                            dS2 += t * t;
+                            nr.w[kk] |= 1u << (i & 31);
+                            if (low) { rl++; kmax_rl = fmaxf(kmax_rl, tk); } else { rh++; kmin_rh = fminf(kmin_rh, tk); }
+                        } else {
+                            if (low) kmin_kl = fminf(kmin_kl, tk); else kmax_kh = fmaxf(kmax_kh, tk);
+                        }
+                    }
+                }
+                // undecidable sample, or rejected and kept candidates not separated in key order (the window is kept by key rank)
+                if (unc || kmax_rl > kmin_kl || kmin_rh < kmax_kh) { slow[h] = done[h] = true; continue; }
+                const int m = b[h] - a[h];
+                const int ni = m - rl - rh;
+                if (ni < nstop || ni == m) { done[h] = true; continue; }             // tools.c:100-103
+                itl[h]--;
+                T1[h] -= dT1;
+                S2[h] -= dS2;
+#pragma unroll
+                for (int kk = 0; kk < W; kk++) rej[h].w[kk] |= nr.w[kk];
+                a[h] += rl;
+                b[h] -= rh;
+            }
+        }
+        __syncwarp();
+
+        // ---- results of the two voxels ------------------------------------------------------------------------
+        int kept[2];
+        double mean[2];
+        ExpSet<NB> drop[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            kept[h] = b[h] - a[h];
+            mean[h] = n[h] > 0 ? p[h] + T1[h] * sm.rcp[kept[h]] : CUDART_NAN;        // merging.c:439
+#pragma unroll
+            for (int kk = 0; kk < W; kk++) {
+                if (slow[h]) rej[h].w[kk] = 0u;                                     // recomputed later: count no rejection here
+                drop[h].w[kk] = inval[h].w[kk] | rej[h].w[kk];
+            }
+        }
+
+        // ---- propagated variance over the kept set (merging.c:431,461-462) ---------------------------------------
+        // STAT rows straight from L2 (prefetched at the start of the tile) into the registers the keys vacated, two
+        // half-batches; float32 FMAs in chains of <= 3 terms, chains summed in float64: <= 4 * 2^-24 relative for
+        // non-negative STAT.  A sign bit among the loaded values (a negative or negative-NaN STAT, kept or not)
+        // sends the lane to float64 products in exposure order.
+        double vsum[2] = {0.0, 0.0};
+        if constexpr (PROP) {
+            constexpr int NACC = (NB + 2) / 3;
+            constexpr int HB = NB / 2;
+            float vacc[2][NACC];
+#pragma unroll
+            for (int j = 0; j < NACC; j++) { vacc[0][j] = 0.f; vacc[1][j] = 0.f; }
+            unsigned neg = 0u;
+            const bool pair_ok = v0 + 1 < A.nvox;
+            if (pair_ok) {
+                const float* vp = S.var0 + v0;
+                float2 sv[NB];
+#pragma unroll
+                for (int i = 0; i < HB; i++) {
+                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
+                    vp += S.vstride;
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int i = HB; i < NB; i++) {
+                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
+                    vp += S.vstride;
+                }
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    if (!drop[0].test(i)) vacc[0][i % NACC] = __fmaf_rn(sv[i].x, S.scale2f[i], vacc[0][i % NACC]);
+                    if (!drop[1].test(i)) vacc[1][i % NACC] = __fmaf_rn(sv[i].y, S.scale2f[i], vacc[1][i % NACC]);
+                    neg |= __float_as_uint(sv[i].x) | __float_as_uint(sv[i].y);
+                }
+#pragma unroll
+                for (int j = 0; j < NACC; j++) { vsum[0] += (double)vacc[0][j]; vsum[1] += (double)vacc[1][j]; }
+            }
+            if (!pair_ok || (neg & 0x80000000u)) {
+                // ragged last pair, or a sign bit was seen: float64 products in exposure order (merging.c:431)
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    vsum[h] = 0.0;
+                    if (v0 + h >= A.nvox) continue;
+                    for (int i = 0; i < A.nfiles; i++)
+                        if (!drop[h].test_dyn(i)) vsum[h] += (double)__ldg(S.var0 + (size_t)i * S.vstride + (v0 + h)) * (sm.os[i].y * sm.os[i].y);
+                }
+            }
+        }
+
+        // ---- per-exposure counters: transpose the lanes' masks, one POPC per lane ----------------------------------
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int kk = 0; kk < W; kk++) {
+                cnt_inval[kk] += __popc(tc.apply(inval[h].w[kk]));
+                cnt_drop[kk] += __popc(tc.apply(drop[h].w[kk]));
+            }
+        }
+        tiles_done++;
+
+        // ---- stores ---------------------------------------------------------------------------------------------
+        double ov[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            if (n[h] == 0) ov[h] = CUDART_NAN;
+            else if (PROP) ov[h] = vsum[h] / ((double)kept[h] * (double)kept[h]);           // merging.c:462
+            else if (kept[h] > 1) {
+                ov[h] = varl[h];                                                            // sigma^2, merging.c:465
+                if (A.typ_var == 1) ov[h] /= (double)(kept[h] - 1);                         // merging.c:467
+            } else ov[h] = CUDART_NAN;
+        }
+        if (v0 + 1 < A.nvox && !slow[0] && !slow[1]) {
+            *reinterpret_cast<double2*>(A.out + v0) = make_double2(mean[0], mean[1]);
+            *reinterpret_cast<double2*>(A.outvar + v0) = make_double2(ov[0], ov[1]);
+            *reinterpret_cast<int2*>(A.expmap + v0) = make_int2(kept[0], kept[1]);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const long long v = v0 + h;
+                if (v >= A.nvox) continue;
+                if (!slow[h]) {
+                    A.out[v] = mean[h];
+                    A.outvar[v] = ov[h];
+                    A.expmap[v] = kept[h];
+                } else {
+                    const unsigned pos = atomicAdd(slow_n, 1u);
+                    if (pos < slow_cap) slow_q[pos] = (unsigned)v;
+                    else exact_voxel_store<NB, UNIT>(S, A, v);       // queue full: recompute in place
+                }
+            }
+        }
+    }
+
+    // ---- flush: valid = voxels seen - invalid, selected = voxels seen - dropped -------------------------------------
+    const unsigned seen = tiles_done * 64u;
+#pragma unroll
+    for (int kk = 0; kk < W; kk++) {
+        const int e = 32 * kk + lane;
+        if (e < A.nfiles) {
+            atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_inval[kk]));
+            atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_drop[kk]));
+        }
+    }
+}
+
+}  // namespace mb

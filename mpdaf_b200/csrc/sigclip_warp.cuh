@@ -95,6 +95,13 @@ struct ExpSet {
     }
     __device__ __forceinline__ void set(int i) { w[i >> 5] |= 1u << (i & 31); }              // i constant after unrolling
     __device__ __forceinline__ bool test(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+    __device__ __forceinline__ bool test_dyn(int i) const
+    {
+        unsigned x = 0u;
+#pragma unroll
+        for (int k = 0; k < W; k++) x = ((i >> 5) == k) ? w[k] : x;
+        return (x >> (i & 31)) & 1u;
+    }
     __device__ __forceinline__ void set_dyn(int i)
     {
 #pragma unroll

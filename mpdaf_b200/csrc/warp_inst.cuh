@@ -11,6 +11,7 @@
 
 #include "launch.h"
 #include "sigclip_warp.cuh"
+#include "sigclip_pair.cuh"
 
 namespace mb {
 
@@ -50,7 +51,8 @@ void fill_tile_args(TileArgs<NB>& s, const Job& j)
 
 // 2-D tensor map over a stack of equally pitched float32 rows: dim 0 = voxels, dim 1 = rows, box 32 x nrows,
 // NaN beyond the last voxel (so the lanes of a ragged last tile see invalid samples).
-inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long long nvox, int nrows, unsigned long long pitch_bytes)
+inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long long nvox, int nrows, unsigned long long pitch_bytes,
+                             unsigned box_voxels = 32u, int box_rows = 0, bool nan_fill = true)
 {
     using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -67,20 +69,98 @@ inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long l
     CUtensorMap map;
     const cuuint64_t dims[2] = {nvox, (cuuint64_t)nrows};
     const cuuint64_t strides[1] = {pitch_bytes};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)nrows};
+    const cuuint32_t box[2] = {box_voxels, (cuuint32_t)(box_rows > 0 ? box_rows : nrows)};
     const cuuint32_t estr[2] = {1u, 1u};
     const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+                               nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return false;
     std::memcpy(&out, &map, sizeof(out));
     return true;
+}
+
+// Pair-packed TMA-pipelined sigma clip (sigclip_pair.cuh): float32 stacks up to 64 deep whose rows are equally
+// pitched and 16-byte aligned.  Returns MPDAF_B200_OK and sets `taken` when the stack qualifies.
+template <int NB>
+int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
+{
+    taken = false;
+    if constexpr (NB > 64) {
+        return MPDAF_B200_OK;
+    } else {
+        static const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;
+        const bool need_var = j.a.typ_var == 0;
+        if (off || j.a.mad || j.median || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL) return MPDAF_B200_OK;
+        auto pitch_of = [&](const void* const* rows) -> unsigned long long {   // elements between rows, 0 = not equally pitched / unaligned
+            if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
+            if (j.nfiles == 1) return (unsigned long long)((j.a.nvox + 3) / 4 * 4);
+            const long long step = static_cast<const char*>(rows[1]) - static_cast<const char*>(rows[0]);
+            if (step < j.a.nvox * 4 || (step & 15) != 0) return 0ull;
+            for (int i = 2; i < j.nfiles; i++)
+                if (static_cast<const char*>(rows[i]) - static_cast<const char*>(rows[i - 1]) != step) return 0ull;
+            return (unsigned long long)(step >> 2);
+        };
+        const unsigned long long dp = pitch_of(j.data), vp = need_var ? pitch_of(j.var) : 0ull;
+        if (dp == 0 || (need_var && vp == 0)) return MPDAF_B200_OK;
+        if ((reinterpret_cast<uintptr_t>(j.a.out) & 15u) || (reinterpret_cast<uintptr_t>(j.a.outvar) & 15u) || (reinterpret_cast<uintptr_t>(j.a.expmap) & 7u))
+            return MPDAF_B200_OK;
+        TmaMaps maps;
+        std::memset(&maps, 0, sizeof(maps));
+        if (!encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * dp, 64u, NB, true)) return MPDAF_B200_OK;
+        if (need_var && !encode_stack_map(maps.stat, j.var[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * vp, 64u, NB, false)) return MPDAF_B200_OK;
+        PairArgs<NB> s;
+        std::memset(&s, 0, sizeof(s));
+        s.data0 = static_cast<const float*>(j.data[0]);
+        s.var0 = need_var ? static_cast<const float*>(j.var[0]) : nullptr;
+        s.dstride = dp;
+        s.vstride = vp;
+        double osmax = 0.0;
+        for (int i = 0; i < NB; i++) {
+            const bool in = i < j.nfiles;
+            const double sc = (in && j.scale) ? j.scale[i] : 1.0, of = (in && j.offset) ? j.offset[i] : 0.0;
+            s.os[i] = make_double2(of, sc);
+            s.osp[i] = of * sc;
+            s.kscale[i] = (float)sc;
+            s.koffset[i] = (float)(of * sc);
+            s.scale2[i] = sc * sc;
+            s.scale2f[i] = (float)(sc * sc);
+            osmax = std::max(osmax, std::fabs(of * sc));
+        }
+        s.osmax = osmax;
+        using Cfg = PairCfg<NB>;
+        std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s>", NB, unit ? "unit" : "scaled");
+        const long long ntiles = (j.a.nvox + 63) / 64;
+        auto launch = [&](auto kernel, auto slow_kernel) -> int {
+            const int smem = (int)sizeof(PairSmem<NB>);
+            MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_CUDA(cudaMemsetAsync(ctx.slow_n, 0, sizeof(unsigned), ctx.stream));
+            const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
+            static const int pair_flags = std::getenv("MPDAF_B200_PAIR_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_PAIR_FLAGS")) : 1;
+            kernel<<<grid, Cfg::threads, smem, ctx.stream>>>(s, j.a, ntiles, ctx.slow_q, ctx.slow_n, ctx.slow_cap, pair_flags, maps);
+            MB_CUDA(cudaGetLastError());
+            // queued voxels (uncertifiable from their keys): the reference algorithm restated literally, one thread each
+            slow_kernel<<<ctx.sm_count * 8, 128, 0, ctx.stream>>>(s, j.a, ctx.slow_q, ctx.slow_n, ctx.slow_cap, ctx.slow);
+            MB_CUDA(cudaGetLastError());
+            ctx.launches += 2;
+            return MPDAF_B200_OK;
+        };
+        taken = true;
+        if (unit) return need_var ? launch(sigclip_pair_kernel<NB, true, true>, sigclip_pair_slow_kernel<NB, true>)
+                                  : launch(sigclip_pair_kernel<NB, true, false>, sigclip_pair_slow_kernel<NB, true>);
+        return need_var ? launch(sigclip_pair_kernel<NB, false, true>, sigclip_pair_slow_kernel<NB, false>)
+                        : launch(sigclip_pair_kernel<NB, false, false>, sigclip_pair_slow_kernel<NB, false>);
+    }
 }
 
 // Warp-tiled sigma clip (sigclip_warp.cuh): the main kernel for float32 stacks up to 128 deep.
 template <int NB>
 int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
 {
+    {
+        bool taken = false;
+        const int rc = launch_pair_impl<NB>(j, unit, ctx, taken);
+        if (rc != MPDAF_B200_OK || taken) return rc;
+    }
     TileArgs<NB> s;
     fill_tile_args(s, j);
     const bool full = (j.nfiles == NB);   // every slot in use: the per-row predicates compile away

@@ -51,8 +51,11 @@ def device_stack(n, shape, seed=1, with_var=True, z0=0, device=0):
     count = nz * ny * nx
     v0 = z0 * ny * nx
     dev = torch.device('cuda', device)
-    data = torch.empty((n, count), dtype=torch.float32, device=dev)
-    var = torch.empty((n, count), dtype=torch.float32, device=dev) if with_var else None
+    # HBM layout: one [n][pitch] allocation per HDU, rows padded to a multiple of 32 samples so that every row
+    # starts on a 128-byte line (TMA needs 16-byte aligned rows; 3681 x 326 x 331 is not a multiple of 4)
+    pitch = (count + 31) // 32 * 32
+    data = torch.empty((n, pitch), dtype=torch.float32, device=dev)[:, :count]
+    var = torch.empty((n, pitch), dtype=torch.float32, device=dev)[:, :count] if with_var else None
     stream = torch.cuda.current_stream(dev).cuda_stream
     for i in range(n):
         fill_device(data[i].data_ptr(), device, DATA, seed, i, v0, count, nx, ny, stream)

@@ -59,6 +59,16 @@ def combine_cuda(data, var=None, scales=None, offsets=None, nmax=2, nclip=5.0, n
             sd = torch.from_numpy(np.stack([a.reshape(-1) for a in data])).to(dev)
             td = list(sd)
             tv = None if var is None else list(torch.from_numpy(np.stack([a.reshape(-1) for a in var])).to(dev))
+        elif location == "device_pitched":    # one [N][pitch] allocation, rows padded to 128-byte lines (the pair kernel's layout)
+            pitch = (nvox + 31) // 32 * 32
+            sd = torch.full((n, pitch), float("nan"), dtype=tdt, device=dev)
+            sd[:, :nvox] = torch.from_numpy(np.stack([a.reshape(-1) for a in data])).to(dev)
+            td = [sd[i, :nvox] for i in range(n)]
+            tv = None
+            if var is not None:
+                sv = torch.full((n, pitch), float("nan"), dtype=tdt, device=dev)
+                sv[:, :nvox] = torch.from_numpy(np.stack([a.reshape(-1) for a in var])).to(dev)
+                tv = [sv[i, :nvox] for i in range(n)]
         elif location == "device_scattered":  # rows at irregular distances inside one pool
             gaps = [0] + [32 * (1 + (7 * i) % 5) for i in range(n)]
             starts = [int(sum(gaps[: i + 1]) + i * nvox) for i in range(n)]
