@@ -392,8 +392,9 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         const unsigned st = k % ST, ph = (k / ST) & 1u;
         float (*dt)[64] = sm.stage[st];
         const long long v0 = (tile << 6) + 2 * lane;            // this lane's voxels: v0, v0 + 1
-        // the STAT tile of these voxels is wanted at the end of the tile: start it on its way into L2 now
+        // the STAT rows of these voxels are read at the end of the tile: start them on their way into L2 now
         if (PROP && lane == 0) tma_prefetch_2d(&M.stat, (int)(tile << 6), 0);
+        const bool pair_ok = v0 + 1 < A.nvox;                   // both voxels exist: 8-byte STAT loads are in bounds
         mbar_wait(&sm.full[st], ph);
 
         // ---- pivot: median of the first three samples (robust against one outlier), else the fourth, else 0
@@ -446,30 +447,28 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                     tf[h] = __fmaf_rn(d, S.kscale[i], S.koffset[i]) - pf[h];
                 }
             }
-            asm("{\n\t.reg .pred q0, q1;\n\t.reg .b32 lo0, hi0, lo1, hi1;\n\t"
-                "cvt.rn.bf16x2.f32 %0, %7, %6;\n\t"                 // high half <- voxel 1
-                "setp.nan.bf16x2 q0|q1, %0, %0;\n\t"
-                "max.bf16x2 %1, %0, %8;\n\t"                        // NaN halves -> sentinel key
-                "mov.b64 {lo0, hi0}, %2;\n\t"
-                "mov.b64 {lo1, hi1}, %3;\n\t"
-                "selp.b32 hi0, 0, hi0, q0;\n\t"
-                "selp.b32 hi1, 0, hi1, q1;\n\t"
-                "mov.b64 %2, {lo0, hi0};\n\t"
-                "mov.b64 %3, {lo1, hi1};\n\t"
-                "@q0 add.u32 %4, %4, %9;\n\t"
-                "@q1 add.u32 %5, %5, %9;\n\t}"
-                : "=r"(ukey[i]), "=r"(key[i]), "+d"(t[0]), "+d"(t[1]), "+r"(inval[0].w[i >> 5]), "+r"(inval[1].w[i >> 5])
-                : "f"(tf[0]), "f"(tf[1]), "r"(0xFF7FFF7Fu), "r"(1u << (i & 31)));
+            {
+                asm("{\n\t.reg .pred q0, q1;\n\t.reg .b32 lo0, hi0, lo1, hi1;\n\t"
+                    "cvt.rn.bf16x2.f32 %0, %7, %6;\n\t"                 // high half <- voxel 1
+                    "setp.nan.bf16x2 q0|q1, %0, %0;\n\t"
+                    "max.bf16x2 %1, %0, %8;\n\t"                        // NaN halves -> sentinel key
+                    "mov.b64 {lo0, hi0}, %2;\n\t"
+                    "mov.b64 {lo1, hi1}, %3;\n\t"
+                    "selp.b32 hi0, 0, hi0, q0;\n\t"
+                    "selp.b32 hi1, 0, hi1, q1;\n\t"
+                    "mov.b64 %2, {lo0, hi0};\n\t"
+                    "mov.b64 %3, {lo1, hi1};\n\t"
+                    "@q0 add.u32 %4, %4, %9;\n\t"
+                    "@q1 add.u32 %5, %5, %9;\n\t}"
+                    : "=r"(ukey[i]), "=r"(key[i]), "+d"(t[0]), "+d"(t[1]), "+r"(inval[0].w[i >> 5]), "+r"(inval[1].w[i >> 5])
+                    : "f"(tf[0]), "f"(tf[1]), "r"(0xFF7FFF7Fu), "r"(1u << (i & 31)));
+            }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 T1[h] += t[h];
                 S2[h] = __fma_rn(t[h], t[h], S2[h]);
             }
         }
-        // ---- the samples are consumed: hand the stage back to the producer --------------------------------------
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[st]);
-
         int n[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -594,9 +593,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                     : "+r"(RL[0][i >> 5]), "+r"(RL[1][i >> 5]), "+r"(RH[0][i >> 5]), "+r"(RH[1][i >> 5])
                     : "r"(ukey[i]), "r"(thr_lo), "r"(thr_hi), "r"(1u << (i & 31)));
             }
-            // ---- part B: the candidates' exact values decide (re-read through L2; the first one of each voxel at once) -----
-            int first[2] = {-1, -1};
-            float dfirst[2] = {0.f, 0.f};
+            // ---- part B: the candidates' exact values decide (their samples are still in the stage) ---------------------
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 int cl = 0, ch = 0;
@@ -612,10 +609,6 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                     ncl[h] = nch[h] = 0;
                 }
                 if ((ncl[h] | nch[h]) == 0) continue;
-#pragma unroll
-                for (int kk = W - 1; kk >= 0; kk--)
-                    if (RL[h][kk] | RH[h][kk]) first[h] = 32 * kk + (__ffs(RL[h][kk] | RH[h][kk]) - 1);
-                dfirst[h] = __ldg(S.data0 + (size_t)first[h] * S.dstride + (v0 + h));
             }
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -633,7 +626,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                         const int i = 32 * kk + (__ffs(mw) - 1);
                         mw &= mw - 1u;
                         const bool low = (RL[h][kk] >> (i & 31)) & 1u;
-                        const float dval = (i == first[h]) ? dfirst[h] : __ldg(S.data0 + (size_t)i * S.dstride + (v0 + h));
+                        const float dval = dt[i][2 * lane + h];
                         const double2 osj = sm.os[i];
                         const float2 ksj = sm.kso[i];
                         const double t = UNIT ? (double)dval - p[h] : __fma_rn((double)dval, osj.y, osj.x * osj.y - p[h]);
@@ -663,12 +656,16 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 T1[h] -= dT1;
                 S2[h] -= dS2;
 #pragma unroll
-                for (int kk = 0; kk < W; kk++) rej[h].w[kk] |= nr.w[kk];
+                for (int kk = 0; kk < W; kk++) {
+                    rej[h].w[kk] |= nr.w[kk];
+                }
                 a[h] += rl;
                 b[h] -= rh;
             }
         }
+        // ---- the samples are consumed: hand the stage back to the producer --------------------------------------
         __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[st]);
 
         // ---- results of the two voxels ------------------------------------------------------------------------
         int kept[2];
@@ -698,7 +695,6 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
 #pragma unroll
             for (int j = 0; j < NACC; j++) { vacc[0][j] = 0.f; vacc[1][j] = 0.f; }
             unsigned neg = 0u;
-            const bool pair_ok = v0 + 1 < A.nvox;
             if (pair_ok) {
                 const float* vp = S.var0 + v0;
                 float2 sv[NB];
