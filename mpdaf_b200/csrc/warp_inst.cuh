@@ -88,7 +88,7 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
     if constexpr (NB > 64) {
         return MPDAF_B200_OK;
     } else {
-        static const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;
+        const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;   // read per call: tests switch kernel families
         const bool need_var = j.a.typ_var == 0;
         if (off || j.a.mad || j.median || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL) return MPDAF_B200_OK;
         auto pitch_of = [&](const void* const* rows) -> unsigned long long {   // elements between rows, 0 = not equally pitched / unaligned

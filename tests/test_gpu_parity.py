@@ -20,9 +20,25 @@ def cuda():
     return cuda_runner
 
 
+def is_main_kernel(name):
+    """The two sigma-clip kernel families for float32 stacks up to 128 deep: the pair-packed TMA-pipelined kernel
+    (sigclip_pair.cuh: equally pitched, 16-byte aligned rows, <= 64 exposures, no MAD) and the warp-tiled one."""
+    return "sigclip_pair<" in name or "sigclip_warp<" in name
+
+
+@pytest.fixture(params=["pair", "warp"])
+def family(request, monkeypatch):
+    """Runs a test once per kernel family (MPDAF_B200_NO_PAIR is read per call)."""
+    if request.param == "warp":
+        monkeypatch.setenv("MPDAF_B200_NO_PAIR", "1")
+    else:
+        monkeypatch.delenv("MPDAF_B200_NO_PAIR", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("location", ["device", "host"])
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 9, 12, 13, 16, 24, 25, 32, 33, 48, 49, 64, 65, 96, 97, 128])
-def test_register_kernels_every_bucket(n, location):
+def test_register_kernels_every_bucket(n, location, family):
     rng = np.random.default_rng(100 + n)
     shape = (6, 11, 13)          # 858 voxels: not a multiple of the block size
     data, var = random_stack(rng, n, shape, nan_frac=0.12, outlier_frac=0.04)
@@ -33,15 +49,18 @@ def test_register_kernels_every_bucket(n, location):
             want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, **kw)
             got = cuda().combine_cuda(data, var, vartype=vartype, nclip=nclip, location=location, **kw)
             assert_same_result(got, want)
-            assert "warp" in cuda().kernel_name()
+            assert is_main_kernel(cuda().kernel_name())
+            if family == "warp" or n > 64:
+                assert "sigclip_warp<" in cuda().kernel_name()
     want = oracle.median_port(data)
     got = cuda().median_cuda(data, location=location)
     assert_same_result(got, want, median=True)
 
 
-def test_unit_scale_path_is_bit_exact():
-    """Voxels without a rejection are identical to the bit (first mean in exposure order);
+def test_unit_scale_path_is_bit_exact(monkeypatch):
+    """Warp kernel: voxels without a rejection are identical to the bit (first mean in exposure order);
     after a rejection the mean comes from shifted moments: <= 1e-12 relative."""
+    monkeypatch.setenv("MPDAF_B200_NO_PAIR", "1")
     rng = np.random.default_rng(5)
     data, var = random_stack(rng, 48, (5, 9, 10), nan_frac=0.05, outlier_frac=0.03)
     for nclip in (5.0, 3.0, 2.0):
@@ -55,7 +74,8 @@ def test_unit_scale_path_is_bit_exact():
         assert (want["select_pix"] < want["valid_pix"]).any()
 
 
-def test_scaled_path_first_mean_is_bit_exact():
+def test_scaled_path_first_mean_is_bit_exact(monkeypatch):
+    monkeypatch.setenv("MPDAF_B200_NO_PAIR", "1")
     rng = np.random.default_rng(6)
     n = 24
     data, var = random_stack(rng, n, (5, 9, 10), nan_frac=0.05, outlier_frac=0.05)
@@ -69,11 +89,32 @@ def test_scaled_path_first_mean_is_bit_exact():
     np.testing.assert_array_equal(got["data"][untouched], want["data"][untouched])
 
 
+@pytest.mark.parametrize("scaled", [False, True])
+def test_pair_kernel_means_within_1e_12(scaled):
+    """Pair kernel: every mean is pivot + sum(w - pivot) / n in float64 (no exposure-order sum of w): within a few ulp
+    of the reference whether or not something was rejected; decisions (expmap, counters) identical."""
+    rng = np.random.default_rng(15)
+    n = 48
+    data, var = random_stack(rng, n, (5, 9, 10), nan_frac=0.05, outlier_frac=0.03)
+    kw = dict(scales=np.linspace(0.5, 2, n), offsets=np.linspace(-3, 3, n)) if scaled else {}
+    for nclip, vartype in ((5.0, "stat_one"), (3.0, "stat_mean"), (2.0, "propagate")):
+        want = oracle.combine_port(data, var, nclip=nclip, vartype=vartype, **kw)
+        got = cuda().combine_cuda(data, var, nclip=nclip, vartype=vartype, location="device_pitched", **kw)
+        assert "sigclip_pair<48," + ("scaled" if scaled else "unit") in cuda().kernel_name()
+        np.testing.assert_array_equal(got["expmap"], want["expmap"])
+        np.testing.assert_array_equal(got["select_pix"], want["select_pix"])
+        np.testing.assert_allclose(got["data"], want["data"], rtol=1e-12, atol=0, equal_nan=True)
+        if vartype != "propagate":
+            np.testing.assert_allclose(got["var"], want["var"], rtol=1e-12, atol=0, equal_nan=True)
+        else:
+            np.testing.assert_allclose(got["var"], want["var"], rtol=3e-7, atol=0, equal_nan=True)   # float32 chains of 3
+
+
 @pytest.mark.parametrize("nmax,lo,up,nstop", [(0, 2.0, 2.0, 2), (1, 1.5, 3.0, 1), (3, 1.0, 1.0, 3),
                                               (2, 3.0, 1.5, 5), (5, 1.2, 1.2, 2), (2, 0.5, 0.5, 1),
                                               (2, 5.0, 5.0, 0), (10, 1.0, 2.0, 2)])
 @pytest.mark.parametrize("ties", [False, True])
-def test_clip_parameters(nmax, lo, up, nstop, ties):
+def test_clip_parameters(nmax, lo, up, nstop, ties, family):
     rng = np.random.default_rng(nmax * 31 + nstop)
     data, var = random_stack(rng, 16, (4, 8, 9), nan_frac=0.2, outlier_frac=0.1, ties=ties)
     if nstop < 1:
@@ -99,7 +140,7 @@ def test_mad_and_deep_stacks(n, vartype):
         if n > 128:
             assert ("generic" if mad else "sigclip_runs") in cuda().kernel_name()
         else:
-            assert "warp" in cuda().kernel_name() and ("mad" in cuda().kernel_name()) == mad
+            assert is_main_kernel(cuda().kernel_name()) and ("mad" in cuda().kernel_name()) == mad
     if n > 64:
         assert_same_result(cuda().median_cuda(data), oracle.median_port(data), median=True)
 
@@ -425,7 +466,7 @@ assert all('tma' in k for k in seen), seen
 print('tma ok', sorted(seen))
 """
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, MPDAF_B200_TMA="1")
+    env = dict(os.environ, MPDAF_B200_TMA="1", MPDAF_B200_NO_PAIR="1")
     res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "tma ok" in res.stdout
