@@ -1,19 +1,20 @@
 #!/usr/bin/env python3
-"""bench.py -- Gvoxel.exposures/s of CubeList.combine (sigma clip) on B200.
+"""bench.py -- Gvoxel.exposures/s of CubeList.combine / CubeList.median on B200.
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
-48 synthetic MUSE-WFM exposures of nz x 326 x 331 voxels (nz = 3681 when the stack
-fits the GPU, else the largest nz that does), float32 DATA + STAT resident in HBM,
-sigma clip nmax=2 nclip=5 nstop=2, var='propagate', per-exposure scales/offsets.
+Workloads (BASELINE.json `configs`; --config picks one, default cfg3 = the configuration the metric is quoted on):
+  cfg2  12 synthetic 3681x326x331 exposures, CubeList.median
+  cfg3  48 synthetic 3681x326x331 exposures, sigma clip nmax=2 nclip=5 nstop=2, var='propagate', scales/offsets
+  cfg4  96 synthetic 3681x326x331 exposures, sigma clip, var='stat_mean'
+float32 DATA (+ STAT) resident in HBM as one [N][pitch] allocation per HDU.
 
   python bench.py --gpus N --steps K --warmup W          (under torchrun for N > 1)
-  python bench.py --impl reference ...                   (the reference's CPU path)
+  python bench.py --impl reference ...                   (the reference's own CPU path, all host threads it can use)
 
-One step = one pass of the hot path over the rank's whole slab.  `value` times the
-device-resident call with CUDA events; `e2e` times the same C-ABI call with HOST
-(pinned) buffers, host<->device copies inside the timed region.  Multi-GPU: one
-process per GPU, each rank combines its own wavelength slab (weak scaling, no
-data-path collective); the per-exposure counters are summed over NCCL every step.
+One step = one pass of the hot path over the whole cube.  With N ranks the ONE cube is sharded along wavelength
+(461 + 7 x 460 planes at N = 8, mpdaf_b200/sharding.py): strong scaling, no data-path collective; the per-exposure
+counters are summed over NCCL every step.  `value` times the device-resident call with CUDA events (max over ranks);
+`e2e` times the same C-ABI call with pinned HOST buffers, host<->device copies inside the timed region, and carries
+the pageable-NumPy and file-name (drop-in symbol, FITS decode included) variants beside it.
 """
 import argparse
 import json
@@ -33,13 +34,24 @@ sys.path.insert(0, ROOT)
 NY, NX = 326, 331
 PLANE = NY * NX
 NZ_FULL = 3681
-NFILES = 48
 CLIP = dict(nmax=2, nclip=5.0, nstop=2)
+CONFIGS = {
+    "cfg2": dict(n=12, median=True, var=None, scaled=False, index=1,
+                 what="12 synthetic {nz}x326x331 cubes, CubeList.median"),
+    "cfg3": dict(n=48, median=False, var="propagate", scaled=True, index=2,
+                 what="48 synthetic {nz}x326x331 cubes, sigma-clip var='propagate' with per-exposure scales/offsets"),
+    "cfg4": dict(n=96, median=False, var="stat_mean", scaled=False, index=3,
+                 what="96 synthetic {nz}x326x331 cubes with var, sigma-clip var='stat_mean'"),
+}
+TYP = {"propagate": 0, "stat_mean": 1, "stat_one": 2, None: 1}
+METRIC = {False: "Gvoxel*exposures/s for CubeList.combine sigma-clip", True: "Gvoxel*exposures/s for CubeList.median"}
+DTYPE = "f64 statistics (float32 samples; bfloat16/float32 sort keys with certified decisions; float32 variance chains)"
 
 
-def algorithmic_bytes_per_voxel(n, propagate=True):
-    """B = N * 4 * a + 20 (float32 samples, f64 data + f64 var + i32 expmap)."""
-    return n * 4 * (2 if propagate else 1) + 20
+def algorithmic_bytes_per_voxel(cfg):
+    """B = N * 4 * a + o (float32 samples; f64 data [+ f64 var] + i32 expmap)."""
+    a = 2 if cfg["var"] == "propagate" else 1
+    return cfg["n"] * 4 * a + (12 if cfg["median"] else 20)
 
 
 def measured_peak():
@@ -106,79 +118,94 @@ def dist_env():
     return rank, world, local
 
 
+def workload_config(name, world):
+    """Identical in both arms: it names the workload, not how much of it a bounded CPU sample covers."""
+    cfg = CONFIGS[name]
+    out = {
+        "workload": "MUSE WFM exposures: " + cfg["what"].format(nz=NZ_FULL) + f" (BASELINE.json configs[{cfg['index']}])",
+        "exposures": cfg["n"], "shape": [NZ_FULL, NY, NX], "input_dtype": "float32",
+        "sharding": f"one cube, wavelength slabs over {world} rank(s)",
+        "l2": "inputs larger than L2 (no flush needed)",
+    }
+    if not cfg["median"]:
+        out.update(nmax=CLIP["nmax"], nclip=CLIP["nclip"], nstop=CLIP["nstop"], var=cfg["var"],
+                   scales_offsets=bool(cfg["scaled"]))
+    return out
+
+
+def scales_offsets(cfg):
+    n = cfg["n"]
+    if cfg["scaled"]:
+        return np.linspace(0.9, 1.1, n), np.linspace(-0.1, 0.1, n)
+    return np.ones(n), np.zeros(n)
+
+
 # ---------------------------------------------------------------------------------------
-# CPU side: the reference's own OpenMP merging.c (oracle/_ref) or the port
+# CPU side: the reference's own OpenMP merging.c (oracle/_ref) or the port.  Nothing here loads the CUDA library.
 # ---------------------------------------------------------------------------------------
-def cpu_sample_setup(nz, tmpdir):
-    """Write the bounded sample as FITS files (float32 BE, DATA + STAT) for the reference."""
-    from mpdaf_b200 import fits as mfits
-    from mpdaf_b200 import synth
+def cpu_sample_setup(cfg, nz, tmpdir):
+    """The bounded sample as FITS files (float32 BE, DATA [+ STAT]) from the NumPy generator."""
+    from mpdaf_b200 import fits as mfits          # pure Python (the package imports its classes lazily)
+    from oracle import synth_np
     files = []
-    for i in range(NFILES):
-        d = synth.fill_host(synth.DATA, 1, i, 0, nz * PLANE, NX, NY).reshape(nz, NY, NX)
-        v = synth.fill_host(synth.STAT, 1, i, 0, nz * PLANE, NX, NY).reshape(nz, NY, NX)
+    for i in range(cfg["n"]):
+        d = synth_np.synth_data_numpy(1, i, 0, nz * PLANE, NX, NY).reshape(nz, NY, NX)
+        v = synth_np.synth_stat_numpy(1, i, 0, nz * PLANE).reshape(nz, NY, NX) if cfg["var"] else None
         path = os.path.join(tmpdir, f"exp-{i:03d}.fits")
         mfits.write_cube(path, d, v)
         files.append(path)
     return files
 
 
-def dropin_files_run(files, nz, scales, offsets, ref_result):
-    """The drop-in symbol itself (`mpdaf_merging_sigma_clipping`, FITS file names in, NumPy buffers
-    out -- exactly the call lib/mpdaf/obj/cubelist.py:512-515 makes) on the same FITS files the
-    reference just combined: wall-clock time including FITS reading, H2D, kernel and D2H."""
-    import ctypes
-    from mpdaf_b200.ctools import ctools
-    nvox = nz * PLANE
-    out, outvar = np.empty(nvox), np.empty(nvox)
-    expmap = np.empty(nvox, dtype=np.intc)
-    names = "\n".join(files).encode("utf8")
-    best = None
-    for _ in range(3):
-        sel, val = np.zeros(NFILES, dtype=np.intc), np.zeros(NFILES, dtype=np.intc)
-        t0 = time.perf_counter()
-        rc = ctools.mpdaf_merging_sigma_clipping(ctypes.c_char_p(names), out, outvar, expmap, scales, offsets, sel, val,
-                                                 CLIP["nmax"], CLIP["nclip"], CLIP["nclip"], CLIP["nstop"], 0, 0)
-        dt = time.perf_counter() - t0
-        if rc != 0:
-            return {"error": f"rc={rc}"}
-        best = dt if best is None else min(best, dt)
-    with np.errstate(invalid="ignore", divide="ignore"):
-        rel = float(np.nanmax(np.abs(out - ref_result["data"]) / np.abs(ref_result["data"])))
-    ok = bool(np.array_equal(expmap, ref_result["expmap"]) and np.array_equal(sel, ref_result["select_pix"])
-              and np.array_equal(val, ref_result["valid_pix"]) and rel <= 1e-6)
-    return {"seconds": best, "value": NFILES * nvox / best / 1e9, "unit": "Gvoxel*exposures/s",
-            "parity_with_reference_ok": ok, "max_rel_err_data": rel,
-            "what": "mpdaf_merging_sigma_clipping(file names) on the reference's own FITS inputs, FITS decode included"}
-
-
-def cpu_reference_run(nz, steps, warmup, keep=False, dropin=False):
-    """Times mpdaf_merging_sigma_clipping of the compiled reference on nz planes of the workload."""
+def cpu_team(cfg):
+    """(team, planes): the reference's effective OpenMP team on this host (merging.c:58-90) when given every core,
+    and a plane count that loads every one of those threads (merging.c:122-126: nloops = nz / team + 1)."""
     import oracle
-    from mpdaf_b200 import synth
+    cores = os.cpu_count() or 1
+    team = oracle.ref_threads(cfg["n"], TYP[cfg["var"]] if not cfg["median"] else 1, omp_threads=cores)
+    return team, max(team * 4 - 1, team + 1)
+
+
+def cpu_reference_run(name, nz, steps, warmup, keep=False):
+    """Times the compiled reference (or the port) on nz planes of the workload.  Returns (summary, result, files, tmpdir)."""
+    import oracle
+    cfg = CONFIGS[name]
     oracle.build()
-    scales, offsets = synth.default_scales(NFILES), synth.default_offsets(NFILES)
+    n = cfg["n"]
+    scales, offsets = scales_offsets(cfg)
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     tmpdir = tempfile.mkdtemp(prefix="mpdaf_b200_cpu_", dir=base)
+    files = None
     try:
+        team, _ = cpu_team(cfg)
         if oracle.have_ref():
             kind = "reference"
-            files = cpu_sample_setup(nz, tmpdir)
-            cores = oracle.ref_threads(NFILES, 0)
+            # launchers such as torchrun export OMP_NUM_THREADS=1: give the reference every core explicitly
+            oracle.set_ref_threads(os.cpu_count() or 1)
+            files = cpu_sample_setup(cfg, nz, tmpdir)
+            nloops = nz // team + 1 if team < nz else 1
+            busy = min(team, (nz + nloops - 1) // nloops)
 
             def run():
-                return oracle.combine_ref(files, (nz, NY, NX), scales=scales, offsets=offsets, vartype="propagate", **CLIP)
-            sample = (f"unmodified src/merging.c (oracle/_ref, -O2 -fopenmp) on {NFILES} x ({nz},{NY},{NX}) float32 "
-                      f"FITS cubes in {base or 'tmp'} via the stand-in fitsio.h (page-cache reads), "
-                      f"effective OpenMP team {cores} of {os.cpu_count()} cores (merging.c:58-90)")
+                if cfg["median"]:
+                    return oracle.median_ref(files, (nz, NY, NX))
+                return oracle.combine_ref(files, (nz, NY, NX), scales=scales, offsets=offsets, vartype=cfg["var"], **CLIP)
+            sample = (f"unmodified src/merging.c (oracle/_ref, -O2 -fopenmp) on {n} x ({nz},{NY},{NX}) float32 FITS cubes in "
+                      f"{base or 'tmp'} via the stand-in fitsio.h (page-cache reads); OpenMP team {team} of {os.cpu_count()} "
+                      f"cores after the reference's own cap (merging.c:58-90), {busy} of them with planes (merging.c:122-126)")
+            cores = team
         else:
             kind = "port"
-            data, var = synth.host_stack(NFILES, (nz, NY, NX), seed=1)
+            from oracle import synth_np
+            data = [synth_np.synth_data_numpy(1, i, 0, nz * PLANE, NX, NY).reshape(nz, NY, NX) for i in range(n)]
+            var = [synth_np.synth_stat_numpy(1, i, 0, nz * PLANE).reshape(nz, NY, NX) for i in range(n)] if cfg["var"] else None
             cores = oracle.port().oracle_num_threads()
 
             def run():
-                return oracle.combine_port(data, var, scales=scales, offsets=offsets, vartype="propagate", **CLIP)
-            sample = f"oracle port (merge_oracle.c, OpenMP {cores} threads) on {NFILES} x ({nz},{NY},{NX}) float32 arrays"
+                if cfg["median"]:
+                    return oracle.median_port(data)
+                return oracle.combine_port(data, var, scales=scales, offsets=offsets, vartype=cfg["var"], **CLIP)
+            sample = f"oracle port (merge_oracle.c, OpenMP {cores} threads) on {n} x ({nz},{NY},{NX}) float32 arrays"
         for _ in range(warmup):
             run()
         times, result = [], None
@@ -186,60 +213,49 @@ def cpu_reference_run(nz, steps, warmup, keep=False, dropin=False):
             t0 = time.perf_counter()
             result = run()
             times.append(time.perf_counter() - t0)
-        extra = None
-        if dropin and kind == "reference":
-            extra = dropin_files_run(files, nz, scales, offsets, result)
-    finally:
-        if not keep:
-            shutil.rmtree(tmpdir, ignore_errors=True)
+    except Exception:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+        raise
+    if not keep:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+        files, tmpdir = None, None
     sec = float(np.mean(times))
-    value = NFILES * nz * PLANE / sec / 1e9
-    return dict(value=value, unit="Gvoxel*exposures/s", cores=cores, kind=kind, sample=sample,
-                seconds_per_pass=sec, dropin_files=extra), result
+    value = n * nz * PLANE / sec / 1e9
+    return dict(value=value, unit="Gvoxel*exposures/s", cores=cores, kind=kind, sample=sample, seconds_per_pass=sec), result, files, tmpdir
 
 
 def run_reference_arm(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    base, _ = cpu_reference_run(args.cpu_nz, args.steps, args.warmup)
+    cfg = CONFIGS[args.config]
+    nz = args.cpu_nz or cpu_team(cfg)[1]
+    base, _, _, _ = cpu_reference_run(args.config, nz, args.steps, args.warmup)
     line = {
         "impl": "reference",
-        "metric": "Gvoxel*exposures/s for CubeList.combine sigma-clip",
+        "metric": METRIC[cfg["median"]],
         "value": base["value"], "unit": "Gvoxel*exposures/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": base["seconds_per_pass"] * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.cpu_nz, 1, bounded_sample=True),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.config, args.gpus),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "Gvoxel*exposures/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "step": f"one pass of the reference over a bounded sample of {nz} planes (throughput per voxel is nz-independent)",
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(nz, world, bounded_sample=False):
-    cfg = {
-        "workload": f"MUSE WFM exposures: {NFILES} synthetic {nz}x{NY}x{NX} cubes per GPU, sigma-clip "
-                    f"var='propagate' with per-exposure scales/offsets (BASELINE.json configs[2])",
-        "exposures": NFILES, "shape": [nz, NY, NX], "nmax": CLIP["nmax"], "nclip": CLIP["nclip"],
-        "nstop": CLIP["nstop"], "var": "propagate", "input_dtype": "float32",
-        "sharding": f"wavelength slabs, {world} rank(s), {nz} planes each",
-        "l2": "inputs larger than L2 (no flush needed)",
-    }
-    if bounded_sample:
-        cfg["note"] = "bounded CPU sample of the same workload (throughput per voxel is nz-independent)"
-    return cfg
 
 
 # ---------------------------------------------------------------------------------------
 # GPU side
 # ---------------------------------------------------------------------------------------
-def pick_nz(torch, device, requested):
+def pick_nz(torch, device, requested, cfg):
     if requested:
         return requested
     free, _ = torch.cuda.mem_get_info(device)
-    per_plane = PLANE * (NFILES * 2 * 4 + 20)
+    planes = cfg["n"] * (2 if cfg["var"] == "propagate" else 1)
+    per_plane = PLANE * (planes * 4 + 20)
     fit = int((free - (6 << 30)) // per_plane)
     return max(8, min(NZ_FULL, fit))
 
@@ -254,6 +270,11 @@ def run_b200_arm(args):
     from mpdaf_b200.ctools import DEVICE, HOST, check, ctools
     from mpdaf_b200.cubelist import _ptr_table
 
+    cfg = CONFIGS[args.config]
+    n = cfg["n"]
+    median = cfg["median"]
+    typ = TYP[cfg["var"]]
+    with_var = cfg["var"] == "propagate"
     rank, world, local = dist_env()
     if args.gpus > 1 and world == 1:
         # not under torchrun: relaunch ourselves the way the driver does
@@ -265,36 +286,48 @@ def run_b200_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # (with NCCL_DEBUG=VERSION in the environment, as on the GPU boxes, NCCL prints its version banner on stdout
-        # before the JSON line; the environment is left as the harness set it)
         dist.init_process_group("nccl", device_id=dev)
 
-    nz = pick_nz(torch, dev, args.nz)
+    # ONE cube of nz_total planes, sharded along wavelength over the ranks (strong scaling)
+    nz_total = args.nz or NZ_FULL
+    z0, z1 = sharding.slab_bounds(nz_total, world, rank)
+    fit = pick_nz(torch, dev, 0, cfg)
+    if z1 - z0 > fit:                                   # does not fit this GPU: shrink the cube for every rank alike
+        nz_total = fit * world
+        z0, z1 = sharding.slab_bounds(nz_total, world, rank)
     if world > 1:
-        t = torch.tensor([nz], device=dev)
+        t = torch.tensor([nz_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        nz = int(t.item())
+        if int(t.item()) != nz_total:
+            nz_total = int(t.item())
+            z0, z1 = sharding.slab_bounds(nz_total, world, rank)
+    nz = z1 - z0
     nvox = nz * PLANE
-    z0 = rank * nz                      # weak scaling: rank r owns planes [r*nz, (r+1)*nz) of a deeper cube
-    stack, tdata, tvar = synth.device_stack(NFILES, (nz, NY, NX), seed=1, with_var=True, z0=z0, device=local)
+    stack, tdata, tvar = synth.device_stack(n, (nz, NY, NX), seed=1, with_var=with_var, z0=z0, device=local)
     out = torch.empty(nvox, dtype=torch.float64, device=dev)
     outvar = torch.empty(nvox, dtype=torch.float64, device=dev)
     expmap = torch.empty(nvox, dtype=torch.int32, device=dev)
-    scales, offsets = synth.default_scales(NFILES), synth.default_offsets(NFILES)
+    scales, offsets = scales_offsets(cfg)
     keep_d, dptr = _ptr_table(stack.data_ptrs)
-    keep_v, vptr = _ptr_table(stack.var_ptrs)
+    keep_v, vptr = _ptr_table(stack.var_ptrs) if with_var else (None, None)
     stream = torch.cuda.current_stream(dev)
-    counters = torch.zeros(2 * NFILES, dtype=torch.int64, device=dev)
+    counters = torch.zeros(2 * n, dtype=torch.int64, device=dev)
     kernel_ms, launches = [], [0]
 
+    def call(location, dp, vp, nv, o, ov, e, strm):
+        valid = np.zeros(n, dtype=np.intc)
+        select = np.zeros(n, dtype=np.intc)
+        if median:
+            rc = ctools.mpdaf_b200_median_arrays(n, dp, 4, nv, location, local, o, e, valid, strm)
+        else:
+            rc = ctools.mpdaf_b200_sigma_clipping_arrays(
+                n, dp, vp, 4, nv, location, local, o, ov, e, scales.ctypes.data, offsets.ctypes.data, select, valid,
+                CLIP["nmax"], CLIP["nclip"], CLIP["nclip"], CLIP["nstop"], typ, 0, strm)
+        check(rc, "merging call")
+        return valid, select
+
     def step(timed=True):
-        valid = np.zeros(NFILES, dtype=np.intc)
-        select = np.zeros(NFILES, dtype=np.intc)
-        rc = ctools.mpdaf_b200_sigma_clipping_arrays(
-            NFILES, dptr, vptr, 4, nvox, DEVICE, local, out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(),
-            scales.ctypes.data, offsets.ctypes.data, select, valid, CLIP["nmax"], CLIP["nclip"], CLIP["nclip"],
-            CLIP["nstop"], 0, 0, stream.cuda_stream)
-        check(rc, "mpdaf_b200_sigma_clipping_arrays")
+        valid, select = call(DEVICE, dptr, vptr, nvox, out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(), stream.cuda_stream)
         if timed:
             kernel_ms.append(ctools.mpdaf_b200_last_kernel_ms())
             launches[0] += ctools.mpdaf_b200_last_launch_count()
@@ -325,117 +358,175 @@ def run_b200_arm(args):
         dist.all_reduce(elapsed, op=dist.ReduceOp.MAX)
         dist.all_reduce(kmean, op=dist.ReduceOp.MAX)
     ms_per_step = float(elapsed.item()) / args.steps
-    value = NFILES * nvox * world / (ms_per_step * 1e-3) / 1e9
+    total_vox = nz_total * PLANE
+    value = n * total_vox / (ms_per_step * 1e-3) / 1e9
 
     # size-independent sanity of the full-size result (cheap, outside the timed region)
-    n_sel = int(select.astype(np.int64).sum())
-    assert n_sel == int(expmap.sum(dtype=torch.int64).item()), "sum(expmap) != sum(selected_pix)"
-    for i in (0, NFILES // 2, NFILES - 1):
+    if not median:
+        n_sel = int(select.astype(np.int64).sum())
+        assert n_sel == int(expmap.sum(dtype=torch.int64).item()), "sum(expmap) != sum(selected_pix)"
+    else:
+        n_sel = int(valid.astype(np.int64).sum())
+        assert n_sel == int(expmap.sum(dtype=torch.int64).item()), "sum(expmap) != sum(valid_pix)"
+    for i in (0, n // 2, n - 1):
         assert int(valid[i]) == nvox - int(torch.isnan(tdata[i]).sum().item()), "valid_pix != #non-NaN samples"
 
     # ---- e2e: same C-ABI call with HOST (pinned) buffers, copies inside the timed region
     nz_e = min(nz, args.e2e_nz)
     nvox_e = nz_e * PLANE
     hd = tdata[:, :nvox_e].cpu().pin_memory()
-    hv = tvar[:, :nvox_e].cpu().pin_memory()
+    hv = tvar[:, :nvox_e].cpu().pin_memory() if with_var else None
     ho = torch.empty(nvox_e, dtype=torch.float64).pin_memory()
     hvv = torch.empty(nvox_e, dtype=torch.float64).pin_memory()
     he = torch.empty(nvox_e, dtype=torch.int32).pin_memory()
-    keep_hd, hdptr = _ptr_table([hd[i].data_ptr() for i in range(NFILES)])
-    keep_hv, hvptr = _ptr_table([hv[i].data_ptr() for i in range(NFILES)])
+    keep_hd, hdptr = _ptr_table([hd[i].data_ptr() for i in range(n)])
+    keep_hv, hvptr = _ptr_table([hv[i].data_ptr() for i in range(n)]) if with_var else (None, None)
 
-    def e2e_step():
-        valid_e = np.zeros(NFILES, dtype=np.intc)
-        select_e = np.zeros(NFILES, dtype=np.intc)
-        rc = ctools.mpdaf_b200_sigma_clipping_arrays(
-            NFILES, hdptr, hvptr, 4, nvox_e, HOST, local, ho.data_ptr(), hvv.data_ptr(), he.data_ptr(),
-            scales.ctypes.data, offsets.ctypes.data, select_e, valid_e, CLIP["nmax"], CLIP["nclip"], CLIP["nclip"],
-            CLIP["nstop"], 0, 0, None)
-        check(rc, "mpdaf_b200_sigma_clipping_arrays[host]")
-        return valid_e, select_e
+    def timed_host_calls(fn, steps):
+        for _ in range(max(1, min(args.warmup, 3))):
+            fn()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize(dev)
+        sec = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return float(sec.item())
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
-    if world > 1:
-        dist.barrier()
     e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_sec = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_sec, op=dist.ReduceOp.MAX)
-    e2e_value = NFILES * nvox_e * world / float(e2e_sec.item()) / 1e9
-    # e2e result must equal the device-resident result on the same planes
+    e2e_sec = timed_host_calls(lambda: call(HOST, hdptr, hvptr, nvox_e, ho.data_ptr(), hvv.data_ptr(), he.data_ptr(), None), e2e_steps)
+    e2e_value = n * nvox_e * world / e2e_sec / 1e9
+    # the e2e result must equal the device-resident result on the same planes
     assert torch.equal(he, expmap[:nvox_e].cpu()), "e2e expmap differs from the device-resident run"
     assert torch.equal(torch.nan_to_num(ho), torch.nan_to_num(out[:nvox_e].cpu())), "e2e data differs"
+    h2d = n * (2 if with_var else 1) * 4 * nvox_e
+    d2h = (12 if median else 20) * nvox_e
+    e2e = {"value": e2e_value, "unit": "Gvoxel*exposures/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "planes_per_rank": nz_e, "seconds_per_step": e2e_sec,
+           "api": "mpdaf_b200_sigma_clipping_arrays / _median_arrays (location=HOST), pinned host buffers, one call per rank"}
+
+    # pageable NumPy buffers: what a caller of the array entry point holds without pinning anything (N = 1 only)
+    if world == 1:
+        pd = [hd[i].numpy().copy() for i in range(n)]
+        pv = [hv[i].numpy().copy() for i in range(n)] if with_var else None
+        po, pvv, pe = np.empty(nvox_e), np.empty(nvox_e), np.empty(nvox_e, dtype=np.intc)
+        kpd, pdptr = _ptr_table([a.ctypes.data for a in pd])
+        kpv, pvptr = _ptr_table([a.ctypes.data for a in pv]) if with_var else (None, None)
+        sec_p = timed_host_calls(lambda: call(HOST, pdptr, pvptr, nvox_e, po.ctypes.data, pvv.ctypes.data, pe.ctypes.data, None), 3)
+        e2e["pageable"] = {"value": n * nvox_e / sec_p / 1e9, "seconds_per_step": sec_p,
+                           "api": "same call, pageable NumPy inputs and outputs (staged through pinned slots by the library)"}
+        del pd, pv
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same planes
-    cpu_baseline, parity, dropin_files = None, None, None
+    # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the same planes + the drop-in symbol on its files
+    cpu_baseline, parity, dropin = None, None, None
     if world == 1 and not args.no_cpu:
-        base, ref = cpu_reference_run(args.cpu_nz, 1, 0, dropin=True)
-        cpu_baseline = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        dropin_files = base.get("dropin_files")
-        nv = args.cpu_nz * PLANE
-        g_exp = expmap[:nv].cpu().numpy()
-        g_dat = out[:nv].cpu().numpy()
-        g_var = outvar[:nv].cpu().numpy()
-        ok_exp = bool(np.array_equal(g_exp, ref["expmap"]))
-        ok_nan = bool(np.array_equal(np.isnan(g_dat), np.isnan(ref["data"])))
-        with np.errstate(invalid="ignore", divide="ignore"):
-            rel_d = np.nanmax(np.abs(g_dat - ref["data"]) / np.abs(ref["data"]))
-            rel_v = np.nanmax(np.abs(g_var - ref["var"]) / np.abs(ref["var"]))
-        parity = {"planes": args.cpu_nz, "expmap_bit_exact": ok_exp, "nan_positions_equal": ok_nan,
-                  "max_rel_err_data": float(rel_d), "max_rel_err_var": float(rel_v),
-                  "ok": bool(ok_exp and ok_nan and rel_d <= 1e-6 and rel_v <= 1e-6)}
+        cpu_nz = min(nz, args.cpu_nz or cpu_team(cfg)[1])
+        base, ref, files, tmpdir = cpu_reference_run(args.config, cpu_nz, 1, 0, keep=True)
+        try:
+            cpu_baseline = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            nv = cpu_nz * PLANE
+            g_exp = expmap[:nv].cpu().numpy()
+            g_dat = out[:nv].cpu().numpy()
+            ok_exp = bool(np.array_equal(g_exp, ref["expmap"]))
+            ok_nan = bool(np.array_equal(np.isnan(g_dat), np.isnan(ref["data"])))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                rel_d = float(np.nanmax(np.abs(g_dat - ref["data"]) / np.abs(ref["data"])))
+            parity = {"planes": cpu_nz, "expmap_bit_exact": ok_exp, "nan_positions_equal": ok_nan, "max_rel_err_data": rel_d}
+            ok = ok_exp and ok_nan and (rel_d == 0.0 if median else rel_d <= 1e-6)
+            if not median:
+                g_var = outvar[:nv].cpu().numpy()
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    rel_v = float(np.nanmax(np.abs(g_var - ref["var"]) / np.abs(ref["var"])))
+                parity["max_rel_err_var"] = rel_v
+                ok = ok and rel_v <= 1e-6
+            parity["ok"] = bool(ok)
+            if files:
+                dropin = dropin_files_run(cfg, files, cpu_nz, scales, offsets, ref)
+        finally:
+            if tmpdir:
+                shutil.rmtree(tmpdir, ignore_errors=True)
+    if dropin:
+        e2e["dropin_files"] = dropin
 
     peak, peak_src = measured_peak()
-    bpv = algorithmic_bytes_per_voxel(NFILES, True)
+    bpv = algorithmic_bytes_per_voxel(cfg)
     kms = float(kmean.item())
-    achieved = bpv * nvox / (kms * 1e-3) / 1e9
-    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
-    # (dram__bytes_read.sum + dram__bytes_write.sum per voxel of the profiled launch, scaled
-    # to this launch's voxel count); null until a capture exists.
+    achieved = bpv * nvox / (kms * 1e-3) / 1e9          # per GPU: the slowest rank's kernel time over its own slab
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             with open(tpath) as f:
-                traffic = float(json.load(f)["dram_bytes_per_voxel"]) * nvox
+                t = json.load(f)
+            if t.get("config", "cfg3") == args.config:
+                traffic = float(t["dram_bytes_per_voxel"]) * nvox
         except Exception:
             traffic = None
     line = {
-        "metric": "Gvoxel*exposures/s for CubeList.combine sigma-clip",
+        "metric": METRIC[median],
         "value": value, "unit": "Gvoxel*exposures/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": workload_config(nz, world),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(args.config, world),
+        "planes_on_device": {"total": nz_total, "this_rank": nz},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
                      "kernel": ctools.mpdaf_b200_last_kernel_name().decode(),
                      "kernel_ms": kms, "algorithmic_bytes_per_voxel": bpv, "voxels_per_launch": nvox,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "cpu_baseline": cpu_baseline,
-        "e2e": {"value": e2e_value, "unit": "Gvoxel*exposures/s",
-                "h2d_bytes_per_step": NFILES * 2 * 4 * nvox_e, "d2h_bytes_per_step": 20 * nvox_e,
-                "planes": nz_e, "seconds_per_step": float(e2e_sec.item()),
-                "api": "mpdaf_b200_sigma_clipping_arrays(location=HOST), pinned host buffers"},
+        "e2e": e2e,
         "gpu_launches": launches[0],
         "clocks": clocks,
         "parity": parity,
-        "dropin_files": dropin_files,
-        "rejected_fraction": float(1.0 - n_sel / max(1, int(valid.astype(np.int64).sum()))),
+        "rejected_fraction": None if median else float(1.0 - n_sel / max(1, int(valid.astype(np.int64).sum()))),
         "exact_fallback_voxels": int(ctools.mpdaf_b200_slow_voxels(local, 0)),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dropin_files_run(cfg, files, nz, scales, offsets, ref_result):
+    """The drop-in symbols themselves (`mpdaf_merging_sigma_clipping` / `mpdaf_merging_median`: FITS file names in, NumPy
+    buffers out -- exactly the calls lib/mpdaf/obj/cubelist.py:456,512-515 make) on the FITS files the reference just
+    combined: wall-clock time including FITS reading, H2D, kernel and D2H."""
+    import ctypes
+    from mpdaf_b200.ctools import ctools
+    n = cfg["n"]
+    nvox = nz * PLANE
+    out, outvar = np.empty(nvox), np.empty(nvox)
+    expmap = np.empty(nvox, dtype=np.intc)
+    names = "\n".join(files).encode("utf8")
+    best = None
+    for _ in range(3):
+        sel, val = np.zeros(n, dtype=np.intc), np.zeros(n, dtype=np.intc)
+        t0 = time.perf_counter()
+        if cfg["median"]:
+            rc = ctools.mpdaf_merging_median(ctypes.c_char_p(names), out, expmap, val)
+        else:
+            rc = ctools.mpdaf_merging_sigma_clipping(ctypes.c_char_p(names), out, outvar, expmap, scales, offsets, sel, val,
+                                                     CLIP["nmax"], CLIP["nclip"], CLIP["nclip"], CLIP["nstop"], TYP[cfg["var"]], 0)
+        dt = time.perf_counter() - t0
+        if rc != 0:
+            return {"error": f"rc={rc}"}
+        best = dt if best is None else min(best, dt)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = float(np.nanmax(np.abs(out - ref_result["data"]) / np.abs(ref_result["data"])))
+    ok = bool(np.array_equal(expmap, ref_result["expmap"]) and np.array_equal(val, ref_result["valid_pix"]) and rel <= 1e-6)
+    if not cfg["median"]:
+        ok = ok and bool(np.array_equal(sel, ref_result["select_pix"]))
+    return {"seconds": best, "value": n * nvox / best / 1e9, "unit": "Gvoxel*exposures/s", "planes": nz,
+            "parity_with_reference_ok": ok, "max_rel_err_data": rel,
+            "api": "the drop-in file-name symbol on the reference's own FITS inputs, FITS decode included"}
 
 
 def main():
@@ -444,9 +535,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--nz", type=int, default=0, help="planes per GPU (default: 3681 or what fits)")
-    ap.add_argument("--e2e-nz", type=int, default=32, help="planes of the host-buffer e2e call")
-    ap.add_argument("--cpu-nz", type=int, default=24, help="planes of the bounded CPU sample")
+    ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
+    ap.add_argument("--nz", type=int, default=0, help="planes of the whole cube (default: 3681 or what fits)")
+    ap.add_argument("--e2e-nz", type=int, default=32, help="planes per rank of the host-buffer e2e call")
+    ap.add_argument("--cpu-nz", type=int, default=0, help="planes of the bounded CPU sample (default: 4 x team - 1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -139,6 +139,20 @@ int mpdaf_b200_last_expmap_histogram(long long *hist, int nbins);
  * on `device` since the last reset (see DESIGN.md "certified decisions"); -1 if unknown. */
 long long mpdaf_b200_slow_voxels(int device, int reset);
 
+/* Devices a HOST-location or file-name call spreads its wavelength slabs over (the reference deals plane ranges to
+ * its OpenMP threads inside the call, merging.c:112-137; here chunk c of consecutive voxels goes to device c % n, each
+ * device with its own staging slots and streams, results land at the chunk's offset of the caller's arrays and the
+ * per-exposure counters are summed at the end).  n = 0 restores the default: MPDAF_B200_DEVICES ("all", a count or a
+ * comma-separated list), else every usable device.  The array entry points take `device` = MPDAF_B200_ALL_DEVICES to use
+ * this set and a device index >= 0 to use exactly that device; the file-name symbols use the set unless MPDAF_B200_DEVICE
+ * names one device. */
+#define MPDAF_B200_ALL_DEVICES (-1)
+int mpdaf_b200_set_devices(int n, const int *ids);
+
+/* Frees everything the library keeps between calls (per-device staging slots: device buffers, pinned host staging,
+ * streams).  A long-lived process calls it when it is done combining; the next call allocates again. */
+int mpdaf_b200_release(void);
+
 /* Number of usable sm_100 devices (0 when none / no driver). */
 int mpdaf_b200_device_count(void);
 const char *mpdaf_b200_last_error(void);

@@ -78,277 +78,6 @@ struct ClipArgs {
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 
-template <typename T>
-__device__ __forceinline__ void cmpxchg(T& a, T& b)
-{
-    const T lo = a < b ? a : b;
-    const T hi = a < b ? b : a;
-    a = lo;
-    b = hi;
-}
-template <>
-__device__ __forceinline__ void cmpxchg<float>(float& a, float& b)
-{
-    const float lo = fminf(a, b);
-    const float hi = fmaxf(a, b);
-    a = lo;
-    b = hi;
-}
-
-template <int NB, typename T>
-__device__ __forceinline__ void sort_stack(T (&a)[NB])
-{
-#define MB_CE(i, j) cmpxchg(a[i], a[j]);
-    if constexpr (NB == 4) { MB_SORTNET_4(MB_CE) }
-    else if constexpr (NB == 8) { MB_SORTNET_8(MB_CE) }
-    else if constexpr (NB == 12) { MB_SORTNET_12(MB_CE) }
-    else if constexpr (NB == 16) { MB_SORTNET_16(MB_CE) }
-    else if constexpr (NB == 24) { MB_SORTNET_24(MB_CE) }
-    else if constexpr (NB == 32) { MB_SORTNET_32(MB_CE) }
-    else if constexpr (NB == 48) { MB_SORTNET_48(MB_CE) }
-    else if constexpr (NB == 64) { MB_SORTNET_64(MB_CE) }
-    else { static_assert(NB == 4, "no sorting network for this stack depth"); }
-#undef MB_CE
-}
-
-// Per-exposure counters: one ballot per exposure, lane (i % 32) keeps the running
-// count of exposure i in register slot i / 32.  Flushed once per thread at the end.
-template <int NB>
-struct LaneCounters {
-    unsigned c[(NB + 31) / 32];
-    __device__ __forceinline__ LaneCounters()
-    {
-#pragma unroll
-        for (int k = 0; k < (NB + 31) / 32; k++) c[k] = 0;
-    }
-    // call only from fully unrolled loops: i must fold to a constant so that
-    // c[i >> 5] stays a register
-    __device__ __forceinline__ void add(int i, bool flag, int lane)
-    {
-        const unsigned b = __ballot_sync(0xffffffffu, flag);
-        if (lane == (i & 31)) c[i >> 5] += __popc(b);
-    }
-    __device__ __forceinline__ void flush(unsigned long long* dst, int nfiles, int lane) const
-    {
-        if (dst == nullptr) return;
-#pragma unroll
-        for (int k = 0; k < (NB + 31) / 32; k++) {
-            const int i = k * 32 + lane;
-            if (i < nfiles && c[k] != 0) atomicAdd(dst + i, (unsigned long long)c[k]);
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------
-// register-resident median  (merging.c:232-253)
-// ---------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(kThreads) median_reg_kernel(const StackArgs<NB> S, const ClipArgs A)
-{
-    const int lane = threadIdx.x & 31;
-    LaneCounters<NB> valid;
-    const long long stride = (long long)gridDim.x * kThreads;
-    for (long long base = (long long)blockIdx.x * kThreads; base < A.nvox; base += stride) {
-        const long long v = base + threadIdx.x;
-        const bool act = v < A.nvox;
-        float k[NB];
-#pragma unroll
-        for (int i = 0; i < NB; i++)
-            k[i] = (act && i < A.nfiles) ? ld_stream((const float*)S.data[i] + v) : CUDART_NAN_F;
-        int n = 0;
-#pragma unroll
-        for (int i = 0; i < NB; i++) {
-            const bool ok = (k[i] == k[i]);
-            n += ok;
-            k[i] = ok ? k[i] : CUDART_INF_F;
-            // counters need warp-wide ballots: done by every lane, active or not
-            valid.add(i, ok, lane);
-        }
-
-        sort_stack<NB>(k);
-        const int ih = n >> 1;
-        const int il = ih - 1 + (n & 1);
-        float xh = 0.f, xl = 0.f;
-#pragma unroll
-        for (int p = 0; p < NB; p++) {
-            xh = (p == ih) ? k[p] : xh;
-            xl = (p == il) ? k[p] : xl;
-        }
-        if (act) {
-            double med = (n & 1) ? (double)xh : ((double)xh + (double)xl) * 0.5;
-            if (n == 0) med = CUDART_NAN;
-            A.out[v] = med;
-            A.expmap[v] = n;
-        }
-    }
-    valid.flush(A.valid_cnt, A.nfiles, lane);
-}
-
-// ---------------------------------------------------------------------------
-// register-resident sigma clip  (merging.c:423-477 + tools.c:82-118)
-//
-// UNIT = every scale is 1 and every offset 0: w == (double)d exactly, so the
-// sort keys are the float32 samples themselves and every comparison against a
-// float64 bound is done exactly in float32 with the bound rounded towards the
-// safe side (k > c  <=>  k > rd(c);  k < c  <=>  k < ru(c) for float k).
-// Otherwise the keys are the float64 values w = (offset + d) * scale.
-// ---------------------------------------------------------------------------
-template <bool UNIT> struct KeyOf { using type = double; };
-template <> struct KeyOf<true> { using type = float; };
-
-template <bool UNIT>
-struct Bound {  // a strict clip window in key space
-    typename KeyOf<UNIT>::type lo, up;
-    __device__ __forceinline__ Bound(double clo, double cup)
-    {
-        if constexpr (UNIT) {
-            lo = __double2float_rd(clo);
-            up = __double2float_ru(cup);
-        } else {
-            lo = clo;
-            up = cup;
-        }
-    }
-};
-
-template <int NB, bool UNIT>
-__global__ void __launch_bounds__(kThreads) sigclip_reg_kernel(const StackArgs<NB> S, const ClipArgs A)
-{
-    using Key = typename KeyOf<UNIT>::type;
-    const int lane = threadIdx.x & 31;
-    LaneCounters<NB> valid, select;
-    const int nstop = A.nstop < 1 ? 1 : A.nstop;
-    const long long stride = (long long)gridDim.x * kThreads;
-
-    for (long long base = (long long)blockIdx.x * kThreads; base < A.nvox; base += stride) {
-        const long long v = base + threadIdx.x;
-        const bool act = v < A.nvox;
-
-        // ---- gather in exposure order (merging.c:425-436)
-        float d[NB];
-#pragma unroll
-        for (int i = 0; i < NB; i++)
-            d[i] = (act && i < A.nfiles) ? ld_stream((const float*)S.data[i] + v) : CUDART_NAN_F;
-
-        Key ws[NB];
-        int n = 0;
-        double sum = 0.0;
-#pragma unroll
-        for (int i = 0; i < NB; i++) {
-            const bool ok = (d[i] == d[i]);
-            double w;
-            if constexpr (UNIT) w = (double)d[i];
-            else w = (S.offset[i] + (double)d[i]) * S.scale[i];
-            n += ok;
-            if (ok) sum += w;                                   // tools.c:13-16, exposure order
-            if constexpr (UNIT) ws[i] = ok ? d[i] : CUDART_INF_F;
-            else ws[i] = ok ? w : CUDART_INF;
-        }
-        double mean = sum / (double)n;                          // n == 0 -> NaN (merging.c:439)
-        double dev = 0.0;
-#pragma unroll
-        for (int i = 0; i < NB; i++) {
-            const bool ok = (d[i] == d[i]);
-            const double t = (double)ws[i] - mean;
-            if (ok) dev += t * t;                               // tools.c:18-21 (no FMA)
-        }
-        double sigma = sqrt(dev / (double)n);
-
-        // ---- order the stack once; later sets are windows [a,b) of it
-        sort_stack<NB>(ws);
-        int a = 0, b = n;
-        Key keepLo, keepUp;                                     // strict bounds of the kept set
-        if constexpr (UNIT) { keepLo = -CUDART_INF_F; keepUp = CUDART_INF_F; }
-        else { keepLo = -CUDART_INF; keepUp = CUDART_INF; }
-
-        if (n >= 2) {
-            int it = A.nmax;
-            for (;;) {
-                const int m = b - a;
-                const int ih = a + (m >> 1);
-                const int il = ih - 1 + (m & 1);
-                Key xh = 0, xl = 0;
-#pragma unroll
-                for (int p = 0; p < NB; p++) {
-                    xh = (p == ih) ? ws[p] : xh;
-                    xl = (p == il) ? ws[p] : xl;
-                }
-                const double med = (m & 1) ? (double)xh : ((double)xh + (double)xl) * 0.5;
-                const double clo = med - (A.nclip_low * sigma);  // tools.c:89-90
-                const double cup = med + (A.nclip_up * sigma);
-                const Bound<UNIT> bd(clo, cup);
-                int ni = 0, nle = 0;
-#pragma unroll
-                for (int p = 0; p < NB; p++) {
-                    const bool inw = (p >= a) && (p < b);
-                    const bool gt = ws[p] > bd.lo;
-                    const bool lt = ws[p] < bd.up;
-                    ni += (inw && gt && lt);
-                    nle += (inw && !gt);
-                }
-                if (ni < nstop || ni == m) break;                // tools.c:100-103
-                if (it <= 0) break;                              // tools.c:104
-                it--;
-                a += nle;
-                b = a + ni;
-                keepLo = bd.lo > keepLo ? bd.lo : keepLo;
-                keepUp = bd.up < keepUp ? bd.up : keepUp;
-                // statistics of the survivors, ascending order (tools.c:116 -> :9-24)
-                double s1 = 0.0;
-#pragma unroll
-                for (int p = 0; p < NB; p++)
-                    if (p >= a && p < b) s1 += (double)ws[p];
-                mean = s1 / (double)ni;
-                double s2 = 0.0;
-#pragma unroll
-                for (int p = 0; p < NB; p++) {
-                    const double t = (double)ws[p] - mean;
-                    if (p >= a && p < b) s2 += t * t;
-                }
-                sigma = sqrt(s2 / (double)ni);
-            }
-        }
-        const int kept = b - a;
-
-        // ---- kept set per exposure, propagated variance, counters
-        double vsum = 0.0;
-#pragma unroll
-        for (int i = 0; i < NB; i++) {
-            const bool ok = (d[i] == d[i]);
-            bool in;
-            if constexpr (UNIT) {
-                in = ok && (d[i] > keepLo) && (d[i] < keepUp);
-            } else {
-                const double w = (S.offset[i] + (double)d[i]) * S.scale[i];
-                in = ok && (w > keepLo) && (w < keepUp);
-            }
-            if (A.typ_var == 0 && i < A.nfiles) {
-                const float sv = act ? ld_stream((const float*)S.var[i] + v) : 0.f;
-                if (in) vsum += (double)sv * S.scale2[i];       // merging.c:431,462
-            }
-            valid.add(i, ok, lane);
-            select.add(i, in, lane);
-        }
-
-        if (act) {
-            double ov;
-            if (A.typ_var == 0) {
-                ov = vsum / ((double)kept * (double)kept);       // merging.c:462
-            } else if (kept > 1) {
-                ov = sigma * sigma;                              // merging.c:465
-                if (A.typ_var == 1) ov /= (double)(kept - 1);    // merging.c:467
-            } else {
-                ov = CUDART_NAN;
-            }
-            A.out[v] = mean;
-            A.outvar[v] = ov;
-            A.expmap[v] = kept;
-        }
-    }
-    valid.flush(A.valid_cnt, A.nfiles, lane);
-    select.flush(A.select_cnt, A.nfiles, lane);
-}
-
 // ---------------------------------------------------------------------------
 // generic kernels: any depth <= kGenericMax, float32 or float64 samples, MAD.
 // Per-thread arrays in local memory; the reference loops restated directly.

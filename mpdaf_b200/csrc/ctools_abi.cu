@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <atomic>
 #include <climits>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -19,7 +21,6 @@
 #include <cuda_runtime.h>
 
 #include "launch.h"
-#include "sigclip_tile.cuh"
 #include "fits_reader.h"
 #include "synth_core.h"
 
@@ -119,72 +120,6 @@ int launch_persistent(Kernel kernel, int device, long long nvox, cudaStream_t st
     return MPDAF_B200_OK;
 }
 
-template <int NB>
-void fill_stack(StackArgs<NB>& s, const Job& j)
-{
-    for (int i = 0; i < NB; i++) {
-        const bool in = i < j.nfiles;
-        s.data[i] = in ? j.data[i] : nullptr;
-        s.var[i] = (in && j.var) ? j.var[i] : nullptr;
-        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
-        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
-        s.scale2[i] = s.scale[i] * s.scale[i];
-    }
-}
-
-template <int NB>
-int launch_reg(const Job& j, bool unit, int device, cudaStream_t stream)
-{
-    StackArgs<NB> s;
-    fill_stack(s, j);
-    char name[64];
-    if (j.median) {
-        std::snprintf(name, sizeof name, "median_reg<%d>", NB);
-        g_last_kernel = name;
-        return launch_persistent(median_reg_kernel<NB>, device, j.a.nvox, stream, s, j.a);
-    }
-    std::snprintf(name, sizeof name, "sigclip_reg<%d,%s>", NB, unit ? "unit" : "scaled");
-    g_last_kernel = name;
-    if (unit) return launch_persistent(sigclip_reg_kernel<NB, true>, device, j.a.nvox, stream, s, j.a);
-    return launch_persistent(sigclip_reg_kernel<NB, false>, device, j.a.nvox, stream, s, j.a);
-}
-
-// Tile-staged sigma clip (sigclip_tile.cuh): the main kernel for float32 stacks up to 64 deep.
-template <int NB>
-int launch_tile(const Job& j, bool unit, int device, cudaStream_t stream)
-{
-    TileArgs<NB> s;
-    bool aligned = true;
-    for (int i = 0; i < NB; i++) {
-        const bool in = i < j.nfiles;
-        s.data[i] = in ? static_cast<const float*>(j.data[i]) : nullptr;
-        s.var[i] = (in && j.var) ? static_cast<const float*>(j.var[i]) : nullptr;
-        s.scale[i] = (in && j.scale) ? j.scale[i] : 1.0;
-        s.offset[i] = (in && j.offset) ? j.offset[i] : 0.0;
-        s.scale2[i] = s.scale[i] * s.scale[i];
-        if (in && (reinterpret_cast<uintptr_t>(s.data[i]) & 15u)) aligned = false;
-        if (in && s.var[i] && (reinterpret_cast<uintptr_t>(s.var[i]) & 15u)) aligned = false;
-    }
-    char name[64];
-    std::snprintf(name, sizeof name, "sigclip_tile<%d,%s,%s>", NB, unit ? "unit" : "scaled", aligned ? "tma" : "ldg");
-    g_last_kernel = name;
-    auto launch = [&](auto kernel) -> int {
-        const int smem = (int)sizeof(TileSmem<NB>);
-        MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int per_sm = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem));
-        if (per_sm < 1) per_sm = 1;
-        const long long ntiles = (j.a.nvox + kThreads - 1) / kThreads;
-        const int grid = (int)std::max(1LL, std::min(ntiles, (long long)g_dev[device].sm_count * per_sm));
-        kernel<<<grid, kThreads, smem, stream>>>(s, j.a, aligned ? 1 : 0, g_dev[device].slow);
-        MB_CUDA(cudaGetLastError());
-        g_last_launches++;
-        return MPDAF_B200_OK;
-    };
-    if (unit) return launch(sigclip_tile_kernel<NB, true>);
-    return launch(sigclip_tile_kernel<NB, false>);
-}
-
 // Uploads the stack description for kernels that read it from device memory.  Ordered on
 // `stream`; no pinned bounce buffer is needed because cudaMemcpyAsync from pageable memory
 // returns after staging the source.
@@ -244,10 +179,9 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         if (j.offset && j.offset[i] != 0.0) unit = false;
     }
     const int nb = bucket_of(j.nfiles);
-    const bool reg_ok = nb != 0 && j.elem == MPDAF_B200_F32;
-    static const std::string which = std::getenv("MPDAF_B200_KERNEL") ? std::getenv("MPDAF_B200_KERNEL") : "warp";
-    const bool use_v1 = which == "reg";
-    if (reg_ok && which == "warp") {
+    // float32 stacks up to 128 deep: the pair-packed kernel where the layout allows it (warp_inst.cuh decides), else
+    // the warp-tiled kernel; one translation unit per depth bucket
+    if (nb != 0 && j.elem == MPDAF_B200_F32) {
         char name[64] = "";
         LaunchCtx ctx;
         ctx.sm_count = g_dev[device].sm_count;
@@ -259,18 +193,6 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         ctx.name = name;
         ctx.name_len = sizeof name;
         int rc = MPDAF_B200_ERR_ARG;
-        const bool no_two_run = std::getenv("MPDAF_B200_NO_TWO_RUN") != nullptr;
-        const bool force_two_run = std::getenv("MPDAF_B200_TWO_RUN") != nullptr;   // read per call (tests toggle it)
-        // two sorted runs (sigclip_warp2.cuh): was the faster kernel for N = 128 with scales/offsets until the
-        // single-network kernel got its lean pass 1 and 256-thread blocks (now 2.34 vs 5.15 ms for 32 planes);
-        // kept as a cross-check, MPDAF_B200_TWO_RUN=1 selects it for every stack deeper than 64
-        if (!j.median && !j.a.mad && nb > 64 && !no_two_run && force_two_run) {
-            rc = upload_table(j, stream);
-            if (rc == MPDAF_B200_OK) rc = nb == 96 ? mb_launch_warp2_48(j, unit, ctx) : mb_launch_warp2_64(j, unit, ctx);
-            g_last_kernel = name;
-            g_last_launches += ctx.launches;
-            return rc;
-        }
         switch (nb) {
 #define MB_CASE(NB) case NB: rc = j.median ? mb_launch_median_warp_##NB(j, ctx) : mb_launch_warp_##NB(j, unit, ctx); break;
             MB_FOR_EACH_DEPTH(MB_CASE)
@@ -280,33 +202,9 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         g_last_launches += ctx.launches;
         return rc;
     }
-    if (reg_ok && !j.median && !use_v1) {
-        switch (nb) {
-            case 4: return launch_tile<4>(j, unit, device, stream);
-            case 8: return launch_tile<8>(j, unit, device, stream);
-            case 12: return launch_tile<12>(j, unit, device, stream);
-            case 16: return launch_tile<16>(j, unit, device, stream);
-            case 24: return launch_tile<24>(j, unit, device, stream);
-            case 32: return launch_tile<32>(j, unit, device, stream);
-            case 48: return launch_tile<48>(j, unit, device, stream);
-            case 64: return launch_tile<64>(j, unit, device, stream);
-        }
-    }
-    if (reg_ok) {
-        switch (nb) {
-            case 4: return launch_reg<4>(j, unit, device, stream);
-            case 8: return launch_reg<8>(j, unit, device, stream);
-            case 12: return launch_reg<12>(j, unit, device, stream);
-            case 16: return launch_reg<16>(j, unit, device, stream);
-            case 24: return launch_reg<24>(j, unit, device, stream);
-            case 32: return launch_reg<32>(j, unit, device, stream);
-            case 48: return launch_reg<48>(j, unit, device, stream);
-            case 64: return launch_reg<64>(j, unit, device, stream);
-        }
-    }
     // 129..512 float32 exposures, plain sigma clip: R sorted runs of 64 (sigclip_runs.cuh)
     if (j.nfiles > 128 && j.nfiles <= kGenericMax && j.elem == MPDAF_B200_F32 && !j.median && !j.a.mad &&
-        which == "warp" && std::getenv("MPDAF_B200_NO_RUNS") == nullptr) {
+        std::getenv("MPDAF_B200_NO_RUNS") == nullptr) {
         char name[64] = "";
         LaunchCtx ctx;
         ctx.sm_count = g_dev[device].sm_count;
@@ -345,6 +243,113 @@ int check_common(int nfiles, const void* const* data, int elem_type, long long n
 // ---------------------------------------------------------------------------
 // slab pipeline: host-resident stacks and FITS files
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// persistent host workers: file reads / gathers of pageable rows into pinned staging
+// ---------------------------------------------------------------------------
+// Created once, on first use, and kept for the life of the process (a drop-in library inside a long-lived
+// Python process used to create and join up to 32 threads per chunk).
+class WorkerPool {
+public:
+    explicit WorkerPool(int n)
+    {
+        for (int t = 0; t < n; t++) threads_.emplace_back([this] { loop(); });
+    }
+    int size() const { return (int)threads_.size(); }
+    // runs fn(0) .. fn(njobs - 1) on the workers (at most `width` of them at a time) and waits for all of them
+    void run(int njobs, int width, const std::function<void(int)>& fn)
+    {
+        if (njobs <= 0) return;
+        std::unique_lock<std::mutex> lk(m_);
+        fn_ = &fn;
+        njobs_ = njobs;
+        next_ = 0;
+        done_ = 0;
+        width_ = std::max(1, std::min(width, size()));
+        generation_++;
+        cv_work_.notify_all();
+        cv_done_.wait(lk, [this] { return done_ == njobs_; });
+        fn_ = nullptr;
+    }
+
+private:
+    void loop()
+    {
+        unsigned long long seen = 0;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_work_.wait(lk, [&] { return generation_ != seen && fn_ != nullptr && next_ < njobs_ && active_ < width_; });
+            const unsigned long long gen = generation_;
+            active_++;
+            while (fn_ != nullptr && generation_ == gen && next_ < njobs_) {
+                const int job = next_++;
+                const std::function<void(int)>* fn = fn_;
+                lk.unlock();
+                (*fn)(job);
+                lk.lock();
+                if (++done_ == njobs_) cv_done_.notify_all();
+            }
+            active_--;
+            if (generation_ == gen) seen = gen;
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int njobs_ = 0, next_ = 0, done_ = 0, width_ = 1, active_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+WorkerPool& worker_pool()
+{
+    static WorkerPool* pool = [] {
+        const long long hw = std::max(1u, std::thread::hardware_concurrency());
+        const char* v = std::getenv("MPDAF_B200_IO_THREADS");
+        const long long want = v ? std::atoll(v) : std::min(32LL, hw);
+        return new WorkerPool((int)std::max(1LL, std::min(64LL, want)));   // never destroyed: its threads end with the process
+    }();
+    return *pool;
+}
+
+// devices a HOST-location / file-name call spreads its wavelength slabs over (mpdaf_b200_set_devices, MPDAF_B200_DEVICES)
+std::vector<int> g_devices;
+
+std::vector<int> usable_devices()
+{
+    std::vector<int> ids;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return ids;
+    for (int i = 0; i < count && i < 16; i++) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, i) == cudaSuccess && prop.major == 10) ids.push_back(i);
+    }
+    return ids;
+}
+
+// "all" | a count | a comma-separated list of device indices
+std::vector<int> parse_devices(const char* spec)
+{
+    std::vector<int> ids;
+    const std::vector<int> all = usable_devices();
+    if (spec == nullptr || *spec == 0) return ids;
+    const std::string sp(spec);
+    if (sp == "all") return all;
+    if (sp.find(',') == std::string::npos) {
+        const int n = std::atoi(sp.c_str());
+        for (int i = 0; i < n && i < (int)all.size(); i++) ids.push_back(all[i]);
+        return ids;
+    }
+    size_t pos = 0;
+    while (pos < sp.size()) {
+        const size_t e = sp.find(',', pos);
+        const std::string tok = sp.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+        if (!tok.empty()) ids.push_back(std::atoi(tok.c_str()));
+        if (e == std::string::npos) break;
+        pos = e + 1;
+    }
+    return ids;
+}
+
 struct Slot {
     cudaStream_t stream = nullptr;
     char* d_in = nullptr;      // [planes][chunk] samples (data planes then var planes)
@@ -399,7 +404,7 @@ int ensure_slot(Slot& s, size_t in_bytes, size_t chunk, bool host_staging)
     if (host_staging && in_bytes > s.host_bytes) {
         if (s.h_in) cudaFreeHost(s.h_in);
         s.host_bytes = 0;
-        MB_CUDA(cudaMallocHost(&s.h_in, in_bytes));
+        MB_CUDA(cudaHostAlloc((void**)&s.h_in, in_bytes, cudaHostAllocPortable));
         s.host_bytes = in_bytes;
     }
     s.timed = false;
@@ -412,7 +417,7 @@ int ensure_out_staging(Slot& s, size_t chunk)
     if (chunk > s.h_out_cap) {
         if (s.h_out) cudaFreeHost(s.h_out);
         s.h_out_cap = 0;
-        MB_CUDA(cudaMallocHost(&s.h_out, chunk * (2 * sizeof(double) + sizeof(int))));
+        MB_CUDA(cudaHostAlloc((void**)&s.h_out, chunk * (2 * sizeof(double) + sizeof(int)), cudaHostAllocPortable));
         s.h_out_cap = chunk;
     }
     return MPDAF_B200_OK;
@@ -443,9 +448,13 @@ long long env_ll(const char* name, long long dflt)
     return v ? std::atoll(v) : dflt;
 }
 
-// Runs the whole stack through `device` in chunks of consecutive voxels.
-int run_slabs(const SlabSource& src, Job job, int device, double* out, double* outvar, int* expmap)
+// Runs the whole stack through the devices in chunks of consecutive voxels (wavelength slabs, merging.c:112-137:
+// the reference deals plane ranges to its OpenMP threads the same way).  Chunk c goes to device c % ndev; every
+// device has its own slots and streams, results are copied straight to the chunk's offset in the caller's arrays,
+// and the per-exposure counters of the devices are summed by run_job.  No data moves between devices.
+int run_slabs(const SlabSource& src, Job job, const std::vector<int>& devs, double* out, double* outvar, int* expmap)
 {
+    const int ndev = (int)devs.size();
     const int nfiles = job.nfiles;
     const bool need_var = !job.median && job.a.typ_var == 0;
     const int planes = nfiles * (need_var ? 2 : 1);
@@ -461,15 +470,18 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     chunk = std::max(1024LL, chunk / 1024 * 1024);
     chunk = std::min(chunk, (nvox + 1023) / 1024 * 1024);
     if (chunk < 1) chunk = 1024;
-    const int nslots = (int)std::max<long long>(1, std::min<long long>(kSlots, (nvox + chunk - 1) / chunk));
+    const long long nchunks = (nvox + chunk - 1) / chunk;
+    const int nslots = (int)std::max<long long>(1, std::min<long long>(kSlots, (nchunks + ndev - 1) / ndev));
 
     // pageable host arrays (plain NumPy) are gathered into the slot's pinned staging by worker threads, like file
     // reads: a copy engine reading pageable memory goes through the driver's own single staging buffer and blocks
     const bool stage_in = from_files || !(is_pinned_host(src.host_data[0]) && (!need_var || is_pinned_host(src.host_var[0])));
-    Slot* slots = g_slots[device];
-    for (int k = 0; k < nslots; k++) {
-        const int rc0 = ensure_slot(slots[k], (size_t)planes * chunk * esz, (size_t)chunk, stage_in);
-        if (rc0 != MPDAF_B200_OK) return rc0;
+    for (int dev : devs) {
+        MB_CUDA(cudaSetDevice(dev));
+        for (int k = 0; k < nslots; k++) {
+            const int rc0 = ensure_slot(g_slots[dev][k], (size_t)planes * chunk * esz, (size_t)chunk, stage_in);
+            if (rc0 != MPDAF_B200_OK) return rc0;
+        }
     }
 
     // byte distance between consecutive host rows when it is the same for all of them (else 0): [0] DATA, [1] STAT
@@ -492,9 +504,12 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     // memory blocks the thread until the chunk's kernel has finished, which serialises read / H2D / kernel / D2H
     const bool stage_out = !(is_pinned_host(out) && (job.median || is_pinned_host(outvar)) && is_pinned_host(expmap));
     if (stage_out)
-        for (int k = 0; k < nslots; k++) {
-            const int rc0 = ensure_out_staging(slots[k], (size_t)chunk);
-            if (rc0 != MPDAF_B200_OK) return rc0;
+        for (int dev : devs) {
+            MB_CUDA(cudaSetDevice(dev));
+            for (int k = 0; k < nslots; k++) {
+                const int rc0 = ensure_out_staging(g_slots[dev][k], (size_t)chunk);
+                if (rc0 != MPDAF_B200_OK) return rc0;
+            }
         }
     auto drain = [&](Slot& s) {
         if (!s.pending) return;
@@ -511,8 +526,10 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
     std::vector<const void*> dptr(planes);
     long long c = 0;
     for (long long v0 = 0; v0 < nvox && rc == MPDAF_B200_OK; v0 += chunk, c++) {
-        Slot& s = slots[c % nslots];
+        const int device = devs[c % ndev];
+        Slot& s = g_slots[device][(c / ndev) % nslots];
         const long long cnt = std::min(chunk, nvox - v0);
+        if (cudaSetDevice(device) != cudaSuccess) { rc = fail(MPDAF_B200_ERR_CUDA, "cudaSetDevice failed"); break; }
         // the slot's previous chunk must have left the device (and its pinned staging)
         if (cudaStreamSynchronize(s.stream) != cudaSuccess) { rc = fail(MPDAF_B200_ERR_CUDA, "slab stream failed"); break; }
         drain(s);
@@ -526,31 +543,23 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
 
         if (stage_in) {
             // parallel pread (files) or memcpy (pageable arrays) of every exposure's range into pinned staging
-            std::atomic<int> next{0}, bad{0};
+            std::atomic<int> bad{0};
             std::string first_err;
             std::mutex err_mutex;
-            auto worker = [&]() {
-                for (;;) {
-                    const int p = next.fetch_add(1);
-                    if (p >= planes) return;
-                    if (!from_files) {
-                        const char* base = (const char*)(p < nfiles ? src.host_data[p] : src.host_var[p - nfiles]);
-                        std::memcpy(s.h_in + (size_t)p * chunk * esz, base + (size_t)v0 * esz, (size_t)cnt * esz);
-                        continue;
-                    }
-                    const mbfits::ImageHdu& h = p < nfiles ? (*src.fits_data)[p] : (*src.fits_var)[p - nfiles];
-                    std::string err;
-                    if (mbfits::read_raw(h, v0, cnt, s.h_in + (size_t)p * chunk * esz, &err) != MPDAF_B200_OK) {
-                        std::lock_guard<std::mutex> lk(err_mutex);
-                        if (!bad.exchange(1)) first_err = err;
-                    }
+            const std::function<void(int)> stage_plane = [&](int p) {
+                if (!from_files) {
+                    const char* base = (const char*)(p < nfiles ? src.host_data[p] : src.host_var[p - nfiles]);
+                    std::memcpy(s.h_in + (size_t)p * chunk * esz, base + (size_t)v0 * esz, (size_t)cnt * esz);
+                    return;
+                }
+                const mbfits::ImageHdu& h = p < nfiles ? (*src.fits_data)[p] : (*src.fits_var)[p - nfiles];
+                std::string err;
+                if (mbfits::read_raw(h, v0, cnt, s.h_in + (size_t)p * chunk * esz, &err) != MPDAF_B200_OK) {
+                    std::lock_guard<std::mutex> lk(err_mutex);
+                    if (!bad.exchange(1)) first_err = err;
                 }
             };
-            const long long hw = std::max(1u, std::thread::hardware_concurrency());
-            const int nthreads = (int)std::min<long long>(planes, std::max(1LL, env_ll("MPDAF_B200_IO_THREADS", std::min(32LL, hw))));
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nthreads; t++) pool.emplace_back(worker);
-            for (auto& t : pool) t.join();
+            worker_pool().run(planes, planes, stage_plane);
             if (bad.load()) { rc = fail(MPDAF_B200_ERR_IO, first_err); break; }
             if (cudaMemcpyAsync(s.d_in, s.h_in, (size_t)planes * chunk * esz, cudaMemcpyHostToDevice, s.stream) != cudaSuccess) {
                 rc = fail(MPDAF_B200_ERR_CUDA, "H2D of a staged slab failed");
@@ -594,6 +603,8 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
         j.slow_q = s.slow_q;
         j.slow_n = s.slow_n;
         j.slow_cap = kSlotQueueCap;
+        j.a.valid_cnt = g_dev[device].counters;
+        j.a.select_cnt = job.median ? nullptr : g_dev[device].counters + kGenericMax;
         j.a.nvox = cnt;
         j.a.out = s.d_out;
         j.a.outvar = s.d_var;
@@ -617,17 +628,21 @@ int run_slabs(const SlabSource& src, Job job, int device, double* out, double* o
             s.pending = true;
         }
     }
-    for (int k = 0; k < nslots; k++) {
-        Slot& s = slots[k];
-        if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc == MPDAF_B200_OK)
-            rc = fail(MPDAF_B200_ERR_CUDA, std::string("slab pipeline: ") + cudaGetErrorString(cudaGetLastError()));
-        if (rc == MPDAF_B200_OK) drain(s);
-        s.pending = false;
-        if (s.timed) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, s.k0, s.k1);
-            kernel_ms += ms;
-            s.timed = false;
+    for (int dev : devs) {
+        cudaSetDevice(dev);
+        for (int k = 0; k < nslots; k++) {
+            Slot& s = g_slots[dev][k];
+            if (!s.stream) continue;
+            if (cudaStreamSynchronize(s.stream) != cudaSuccess && rc == MPDAF_B200_OK)
+                rc = fail(MPDAF_B200_ERR_CUDA, std::string("slab pipeline: ") + cudaGetErrorString(cudaGetLastError()));
+            if (rc == MPDAF_B200_OK) drain(s);
+            s.pending = false;
+            if (s.timed) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, s.k0, s.k1);
+                kernel_ms += ms;
+                s.timed = false;
+            }
         }
     }
     g_last_kernel_ms = kernel_ms;
@@ -644,25 +659,52 @@ struct CounterSink {
     long long* select64 = nullptr;
 };
 
+// restores the caller's current device when a call returns (torch and other CUDA users share the thread's context)
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { saved = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+};
+
+// devices of a HOST-location call: `device` >= 0 names one; MPDAF_B200_ALL_DEVICES (-1) means the configured set
+// (mpdaf_b200_set_devices, else the environment's MPDAF_B200_DEVICES, else every usable device)
+std::vector<int> devices_for(int device)
+{
+    if (device >= 0) return {device};
+    if (!g_devices.empty()) return g_devices;
+    std::vector<int> ids = parse_devices(std::getenv("MPDAF_B200_DEVICES"));
+    if (ids.empty()) ids = usable_devices();
+    return ids;
+}
+
 int run_job(Job job, const SlabSource* slab_src, int location, int device, double* out, double* outvar,
             int* expmap, CounterSink sink, cudaStream_t stream)
 {
     std::lock_guard<std::mutex> lock(g_call_mutex);
+    DeviceGuard guard;
     g_last_launches = 0;
     g_last_kernel_ms = 0.0;
-    int rc = device_ready(device);
-    if (rc != MPDAF_B200_OK) return rc;
-    DeviceState& d = g_dev[device];
+    std::vector<int> devs = location == MPDAF_B200_DEVICE ? std::vector<int>{device} : devices_for(device);
+    if (devs.empty()) return fail(MPDAF_B200_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+    if (location == MPDAF_B200_DEVICE && device < 0) return fail(MPDAF_B200_ERR_ARG, "a DEVICE-location call needs a device index");
+    // no more devices than chunks of work
     const int nfiles = job.nfiles;
-    job.a.valid_cnt = d.counters;
-    job.a.select_cnt = job.median ? nullptr : d.counters + kGenericMax;
-
-    cudaStream_t cstream = (location == MPDAF_B200_DEVICE) ? stream : nullptr;
-    MB_CUDA(cudaMemsetAsync(d.counters, 0, 2 * kGenericMax * sizeof(unsigned long long), cstream));
-    MB_CUDA(cudaMemsetAsync(d.hist, 0, (kGenericMax + 1) * sizeof(unsigned long long), cstream));
     static const bool hist_off = std::getenv("MPDAF_B200_NO_HISTOGRAM") != nullptr;
     g_hist_enabled = !hist_off;
+    cudaStream_t cstream = (location == MPDAF_B200_DEVICE) ? stream : nullptr;
+    for (int dev : devs) {
+        const int rc = device_ready(dev);
+        if (rc != MPDAF_B200_OK) return rc;
+        DeviceState& d = g_dev[dev];
+        MB_CUDA(cudaMemsetAsync(d.counters, 0, 2 * kGenericMax * sizeof(unsigned long long), cstream));
+        MB_CUDA(cudaMemsetAsync(d.hist, 0, (kGenericMax + 1) * sizeof(unsigned long long), cstream));
+        if (location != MPDAF_B200_DEVICE) MB_CUDA(cudaStreamSynchronize(cstream));   // counters zeroed before the slab streams start
+    }
+    int rc = MPDAF_B200_OK;
     if (location == MPDAF_B200_DEVICE) {
+        DeviceState& d = g_dev[device];
+        job.a.valid_cnt = d.counters;
+        job.a.select_cnt = job.median ? nullptr : d.counters + kGenericMax;
         job.table_dev = d.table;
         job.a.out = out;
         job.a.outvar = outvar;
@@ -673,29 +715,35 @@ int run_job(Job job, const SlabSource* slab_src, int location, int device, doubl
             if (rc != MPDAF_B200_OK) return rc;
             MB_CUDA(cudaEventRecord(d.ev1, stream));
         }
-    } else {
-        MB_CUDA(cudaStreamSynchronize(cstream));  // counters zeroed before the slab streams start
-        if (job.a.nvox > 0) {
-            rc = run_slabs(*slab_src, job, device, out, outvar, expmap);
-            if (rc != MPDAF_B200_OK) return rc;
-        }
+    } else if (job.a.nvox > 0) {
+        rc = run_slabs(*slab_src, job, devs, out, outvar, expmap);
+        if (rc != MPDAF_B200_OK) return rc;
     }
-    unsigned long long host_counts[2 * kGenericMax];
-    MB_CUDA(cudaMemcpyAsync(host_counts, d.counters, sizeof host_counts, cudaMemcpyDeviceToHost, cstream));
-    MB_CUDA(cudaMemcpyAsync(g_last_hist, d.hist, sizeof g_last_hist, cudaMemcpyDeviceToHost, cstream));
-    MB_CUDA(cudaStreamSynchronize(cstream));
+    // per-exposure counters and the exposure-map histogram: summed over the devices (the path's only reduction)
+    std::vector<unsigned long long> total(2 * kGenericMax, 0ull), part(2 * kGenericMax);
+    std::vector<unsigned long long> hist_part(kGenericMax + 1);
+    for (int i = 0; i <= kGenericMax; i++) g_last_hist[i] = 0ull;
+    for (int dev : devs) {
+        MB_CUDA(cudaSetDevice(dev));
+        DeviceState& d = g_dev[dev];
+        MB_CUDA(cudaMemcpyAsync(part.data(), d.counters, part.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cstream));
+        MB_CUDA(cudaMemcpyAsync(hist_part.data(), d.hist, hist_part.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cstream));
+        MB_CUDA(cudaStreamSynchronize(cstream));
+        for (size_t i = 0; i < total.size(); i++) total[i] += part[i];
+        for (int i = 0; i <= kGenericMax; i++) g_last_hist[i] += hist_part[i];
+    }
     if (location == MPDAF_B200_DEVICE && job.a.nvox > 0) {
         float ms = 0.f;
-        MB_CUDA(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+        MB_CUDA(cudaEventElapsedTime(&ms, g_dev[device].ev0, g_dev[device].ev1));
         g_last_kernel_ms = ms;
     }
     for (int i = 0; i < nfiles; i++) {
-        const unsigned long long v = host_counts[i], s = host_counts[kGenericMax + i];
+        const unsigned long long v = total[i], sl = total[kGenericMax + i];
         if (sink.valid32) sink.valid32[i] += (int)v;
         if (sink.valid64) sink.valid64[i] += (long long)v;
         if (!job.median) {
-            if (sink.select32) sink.select32[i] += (int)s;
-            if (sink.select64) sink.select64[i] += (long long)s;
+            if (sink.select32) sink.select32[i] += (int)sl;
+            if (sink.select64) sink.select64[i] += (long long)sl;
         }
     }
     return MPDAF_B200_OK;
@@ -732,8 +780,22 @@ int open_all(const std::vector<std::string>& names, const char* ext, std::vector
     return MPDAF_B200_OK;
 }
 
+int merge_files_impl(char* input, bool median, double* data, double* var, int* expmap, double* scale, double* offset,
+                     int* selected_pix, int* valid_pix, int nmax, double lo, double up, int nstop, int typ_var, int mad);
+
 int merge_files(char* input, bool median, double* data, double* var, int* expmap, double* scale, double* offset,
                 int* selected_pix, int* valid_pix, int nmax, double lo, double up, int nstop, int typ_var, int mad)
+{
+    const int rc = merge_files_impl(input, median, data, var, expmap, scale, offset, selected_pix, valid_pix, nmax, lo, up,
+                                    nstop, typ_var, mad);
+    // failures before the cube shape is known cannot fill the outputs; MPDAF_B200_EXIT_ON_ERROR restores the
+    // reference's behaviour (exit) for callers that never look at the return value
+    if (rc != MPDAF_B200_OK && std::getenv("MPDAF_B200_EXIT_ON_ERROR")) std::exit(EXIT_FAILURE);
+    return rc;
+}
+
+int merge_files_impl(char* input, bool median, double* data, double* var, int* expmap, double* scale, double* offset,
+                     int* selected_pix, int* valid_pix, int nmax, double lo, double up, int nstop, int typ_var, int mad)
 {
     if (!input || !data || !expmap || !valid_pix) return fail(MPDAF_B200_ERR_ARG, "null argument");
     if (!median && (!var || !selected_pix)) return fail(MPDAF_B200_ERR_ARG, "null argument");
@@ -745,12 +807,23 @@ int merge_files(char* input, bool median, double* data, double* var, int* expmap
         std::vector<mbfits::ImageHdu>&a, &b;
         ~Closer() { for (auto& h : a) mbfits::close_image(&h); for (auto& h : b) mbfits::close_image(&h); }
     } closer{hd, hv};
+    auto fill_failed = [&](int code) {
+        // the first cube's shape is what the caller allocated for (cubelist.py:447-452)
+        if (!hd.empty()) {
+            const long long nv = hd[0].naxes[0] * hd[0].naxes[1] * hd[0].naxes[2];
+            const double nan = std::nan("");
+            for (long long i = 0; i < nv; i++) data[i] = nan;
+            if (var) for (long long i = 0; i < nv; i++) var[i] = nan;
+            for (long long i = 0; i < nv; i++) expmap[i] = 0;
+        }
+        return code;
+    };
     int rc = open_all(names, "DATA", hd, nullptr);
-    if (rc != MPDAF_B200_OK) return rc;
+    if (rc != MPDAF_B200_OK) return fill_failed(rc);
     if (!median && typ_var == 0) {
         rc = open_all(names, "STAT", hv, hd[0].naxes);
-        if (rc != MPDAF_B200_OK) return rc;
-        if (hv[0].bitpix != hd[0].bitpix) return fail(MPDAF_B200_ERR_SHAPE, "DATA and STAT differ in BITPIX");
+        if (rc != MPDAF_B200_OK) return fill_failed(rc);
+        if (hv[0].bitpix != hd[0].bitpix) return fill_failed(fail(MPDAF_B200_ERR_SHAPE, "DATA and STAT differ in BITPIX"));
     }
     Job job;
     job.nfiles = (int)names.size();
@@ -772,8 +845,21 @@ int merge_files(char* input, bool median, double* data, double* var, int* expmap
     CounterSink sink;
     sink.valid32 = valid_pix;
     sink.select32 = selected_pix;
-    const int device = (int)env_ll("MPDAF_B200_DEVICE", 0);
-    return run_job(job, &src, MPDAF_B200_HOST, device, data, var, expmap, sink, nullptr);
+    // MPDAF_B200_DEVICE pins the call to one device; otherwise the slabs are spread over every usable device
+    // (MPDAF_B200_DEVICES = "all" | count | list narrows that down)
+    const int device = std::getenv("MPDAF_B200_DEVICE") ? (int)env_ll("MPDAF_B200_DEVICE", 0) : MPDAF_B200_ALL_DEVICES;
+    const long long nvox = job.a.nvox;
+    rc = run_job(job, &src, MPDAF_B200_HOST, device, data, var, expmap, sink, nullptr);
+    if (rc != MPDAF_B200_OK) {
+        // The reference exits the process on any failure (merging.c:99-108,196-199) and its Python caller ignores the
+        // return value (cubelist.py:456,512): never leave caller-allocated np.empty buffers half written.
+        const double nan = std::nan("");
+        for (long long i = 0; i < nvox; i++) data[i] = nan;
+        if (var) for (long long i = 0; i < nvox; i++) var[i] = nan;
+        for (long long i = 0; i < nvox; i++) expmap[i] = 0;
+        if (std::getenv("MPDAF_B200_EXIT_ON_ERROR")) std::exit(EXIT_FAILURE);
+    }
+    return rc;
 }
 
 int merge_arrays(int nfiles, const void* const* data, const void* const* var, int elem_type, long long nvox,
@@ -878,6 +964,53 @@ int mpdaf_b200_median_arrays(int nfiles, const void* const* data, int elem_type,
                         nullptr, nullptr, sink, 0, 0, 0, 1, 1, 0, stream);
 }
 
+int mpdaf_b200_set_devices(int n, const int* ids)
+{
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    if (n < 0 || (n > 0 && ids == nullptr)) return fail(MPDAF_B200_ERR_ARG, "bad device list");
+    const std::vector<int> usable = usable_devices();
+    std::vector<int> want;
+    for (int i = 0; i < n; i++) {
+        if (std::find(usable.begin(), usable.end(), ids[i]) == usable.end()) return fail(MPDAF_B200_ERR_ARG, "not a usable sm_100 device");
+        if (std::find(want.begin(), want.end(), ids[i]) == want.end()) want.push_back(ids[i]);
+    }
+    g_devices = want;   // empty: back to the default (MPDAF_B200_DEVICES, else every usable device)
+    return MPDAF_B200_OK;
+}
+
+// Frees what the library keeps between calls: the per-device staging slots (device buffers, pinned host staging,
+// streams, events) and the per-device scratch.  The next call allocates again.
+int mpdaf_b200_release(void)
+{
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    DeviceGuard guard;
+    for (int dev = 0; dev < 16; dev++) {
+        bool any = g_dev[dev].ready;
+        for (int k = 0; k < kSlots; k++) any = any || g_slots[dev][k].stream != nullptr;
+        if (!any || cudaSetDevice(dev) != cudaSuccess) continue;
+        cudaDeviceSynchronize();
+        for (int k = 0; k < kSlots; k++) {
+            Slot& s = g_slots[dev][k];
+            if (!s.stream) continue;
+            cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_var); cudaFree(s.d_exp); cudaFree(s.d_table);
+            cudaFree(s.slow_q); cudaFree(s.slow_n);
+            if (s.h_in) cudaFreeHost(s.h_in);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            cudaEventDestroy(s.k0); cudaEventDestroy(s.k1);
+            cudaStreamDestroy(s.stream);
+            s = Slot();
+        }
+        DeviceState& d = g_dev[dev];
+        if (d.ready) {
+            cudaFree(d.counters); cudaFree(d.table); cudaFree(d.slow); cudaFree(d.slow_q); cudaFree(d.slow_n); cudaFree(d.hist);
+            cudaEventDestroy(d.ev0); cudaEventDestroy(d.ev1);
+            d = DeviceState();
+        }
+    }
+    cudaGetLastError();
+    return MPDAF_B200_OK;
+}
+
 double mpdaf_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
 
 int mpdaf_b200_last_expmap_histogram(long long* hist, int nbins)
@@ -890,6 +1023,7 @@ int mpdaf_b200_last_expmap_histogram(long long* hist, int nbins)
 long long mpdaf_b200_slow_voxels(int device, int reset)
 {
     if (device < 0 || device >= 16 || !g_dev[device].ready) return -1;
+    DeviceGuard guard;
     unsigned long long v = 0;
     if (cudaSetDevice(device) != cudaSuccess) return -1;
     if (cudaMemcpy(&v, g_dev[device].slow, sizeof v, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
@@ -945,6 +1079,7 @@ int mpdaf_b200_synth_fill(void* dst, int location, int device, int kind, unsigne
         for (auto& th : pool) th.join();
         return MPDAF_B200_OK;
     }
+    DeviceGuard guard;
     const int rc = device_ready(device);
     if (rc != MPDAF_B200_OK) return rc;
     if (count == 0) return MPDAF_B200_OK;

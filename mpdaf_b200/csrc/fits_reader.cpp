@@ -5,9 +5,11 @@
 #include "fits_reader.h"
 
 #include <cctype>
+#include <cerrno>
 #include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
+#include <sys/resource.h>
 #include <unistd.h>
 
 #include "../../include/mpdaf_b200.h"
@@ -28,6 +30,7 @@ std::string keyword_of(const char* card)
 bool has_value(const char* card) { return card[8] == '=' && card[9] == ' '; }
 
 long long int_value(const char* card) { return std::atoll(std::string(card + 10, 70).c_str()); }
+double real_value(const char* card) { return std::atof(std::string(card + 10, 70).c_str()); }
 
 std::string string_value(const char* card)
 {
@@ -60,8 +63,16 @@ bool iequal(const std::string& a, const std::string& b)
 int open_image(const std::string& path, const std::string& extname, ImageHdu* out, std::string* err)
 {
     int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0 && errno == EMFILE) {
+        // 500 files x (DATA + STAT) is more than the usual soft limit of 1024 descriptors: raise it to the hard limit once
+        struct rlimit rl;
+        if (getrlimit(RLIMIT_NOFILE, &rl) == 0 && rl.rlim_cur < rl.rlim_max) {
+            rl.rlim_cur = rl.rlim_max;
+            if (setrlimit(RLIMIT_NOFILE, &rl) == 0) fd = ::open(path.c_str(), O_RDONLY);
+        }
+    }
     if (fd < 0) {
-        *err = "cannot open " + path;
+        *err = (errno == EMFILE ? "too many open files (RLIMIT_NOFILE) opening " : "cannot open ") + path;
         return MPDAF_B200_ERR_IO;
     }
     long long off = 0;
@@ -69,6 +80,7 @@ int open_image(const std::string& path, const std::string& extname, ImageHdu* ou
     for (int hdu = 0;; hdu++) {
         int bitpix = 0, naxis = 0;
         long long ax[8] = {0}, pcount = 0, gcount = 1;
+        double bscale = 1.0, bzero = 0.0;
         std::string name;
         bool done = false;
         while (!done) {
@@ -88,12 +100,19 @@ int open_image(const std::string& path, const std::string& extname, ImageHdu* ou
                 else if (key == "PCOUNT") pcount = int_value(card);
                 else if (key == "GCOUNT") gcount = int_value(card);
                 else if (key == "EXTNAME") name = string_value(card);
-                else if (key.size() == 6 && key.compare(0, 5, "NAXIS") == 0 && std::isdigit((unsigned char)key[5]))
-                    ax[key[5] - '1'] = int_value(card);
+                else if (key == "BSCALE") bscale = real_value(card);
+                else if (key == "BZERO") bzero = real_value(card);
+                else if (key.size() == 6 && key.compare(0, 5, "NAXIS") == 0 && key[5] >= '1' && key[5] <= '8')
+                    ax[key[5] - '1'] = int_value(card);   // NAXIS1 .. NAXIS8 only: a NAXIS0 / NAXIS9 card must not index ax[]
             }
         }
+        if (naxis < 0 || naxis > 8) {
+            ::close(fd);
+            *err = path + ": NAXIS out of range";
+            return MPDAF_B200_ERR_IO;
+        }
         long long nelem = naxis > 0 ? 1 : 0;
-        for (int k = 0; k < naxis && k < 8; k++) nelem *= ax[k];
+        for (int k = 0; k < naxis; k++) nelem *= ax[k];
         const long long bytes = (std::llabs((long long)bitpix) / 8) * gcount * (pcount + nelem);
         if ((extname.empty() && hdu == 0) || (!extname.empty() && iequal(name, extname))) {
             if (naxis != 3) {  // merging.c:104-107
@@ -104,6 +123,16 @@ int open_image(const std::string& path, const std::string& extname, ImageHdu* ou
             if (bitpix != -32 && bitpix != -64) {
                 ::close(fd);
                 *err = path + "[" + extname + "]: only BITPIX -32/-64 images are supported";
+                return MPDAF_B200_ERR_IO;
+            }
+            if (bscale != 1.0 || bzero != 0.0) {   // cfitsio would apply them while reading (merging.c:228); this reader does not
+                ::close(fd);
+                *err = path + "[" + extname + "]: scaled images (BSCALE / BZERO) are not supported";
+                return MPDAF_B200_ERR_IO;
+            }
+            if (ax[0] < 0 || ax[1] < 0 || ax[2] < 0) {
+                ::close(fd);
+                *err = path + "[" + extname + "]: negative axis length";
                 return MPDAF_B200_ERR_IO;
             }
             out->fd = fd;

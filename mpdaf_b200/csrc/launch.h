@@ -57,8 +57,5 @@ int fail(int code, const std::string& msg);   // records the message (ctools_abi
     int mb_launch_median_warp_##NB(const mb::Job& j, mb::LaunchCtx& ctx);
 MB_FOR_EACH_DEPTH(MB_DECLARE_DEPTH)
 #undef MB_DECLARE_DEPTH
-// two-run kernels for deep stacks (sigclip_warp2.cuh); the stack table must already be on the device
-int mb_launch_warp2_48(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);
-int mb_launch_warp2_64(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);
-// multi-run kernel for 129..512 exposures (sigclip_runs.cuh); same precondition
+// multi-run kernel for 129..512 exposures (sigclip_runs.cuh); the stack table must already be on the device
 int mb_launch_runs(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);

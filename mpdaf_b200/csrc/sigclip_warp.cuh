@@ -33,7 +33,7 @@
 #pragma once
 
 #include "combine_kernels.cuh"
-#include "sigclip_tile.cuh"
+#include "stack_common.cuh"
 
 #ifndef MB_WARP_THREADS
 #define MB_WARP_THREADS 0     // 0: per-depth default (WarpThreads below); otherwise threads per block of the warp kernel
@@ -136,16 +136,16 @@ struct WarpSmem {
     float k[NB][32];   // sorted keys, one column per lane
 };
 
-constexpr int kWT = 128;   // block size of the deep-stack kernels (sigclip_warp2.cuh, sigclip_runs.cuh)
+constexpr int kWT = 128;   // block size of the deep-stack kernel (sigclip_runs.cuh)
 
 // Block size of the warp kernel.  One block per SM holding all its resident warps (1024 threads at 64 registers
 // for depths <= 24, 768 at 80 for depths <= 48): the per-tile barrier then keeps every warp of the SM in the same part of the ~45 KB loop
 // body, which exceeds the 32 KB instruction cache (measured +8 % over 128-thread blocks at N = 48, +11 % at
-// N = 12).  The MAD and TMA variants are shared-memory bound and stay at 128 threads.
-template <int NB, bool MAD, bool TMA>
+// N = 12).  The MAD variant is shared-memory bound and stays at 128 threads.
+template <int NB, bool MAD>
 struct WarpThreads {
     static constexpr int value = MB_WARP_THREADS ? MB_WARP_THREADS
-                                 : ((MAD || TMA) ? 128 : (NB <= 24 ? 1024 : (NB <= 48 ? 768 : (NB <= 64 ? 512 : (NB <= 96 ? 384 : 256)))));
+                                   : (MAD ? 128 : (NB <= 24 ? 1024 : (NB <= 48 ? 768 : (NB <= 64 ? 512 : (NB <= 96 ? 384 : 256)))));
 };
 
 // 128-byte opaque image of a CUtensorMap (filled on the host by cuTensorMapEncodeTiled)
@@ -162,12 +162,10 @@ __device__ __forceinline__ void tma_prefetch_2d(const TensorMap2D* map, int c0, 
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int NB, bool MAD = false, bool TMA = false>
+template <int NB, bool MAD = false>
 struct BlockSmem {
-    static constexpr int kWT = WarpThreads<NB, MAD, TMA>::value;
-    WarpSmem<NB> w[kWT / 32];                            // TMA: also the landing buffer of the DATA tile
-    float v[TMA ? kWT / 32 : 1][TMA ? NB : 1][32];       // TMA: landing buffer of the STAT tile (128-byte aligned)
-    unsigned long long bar[kWT / 32][2];                 // TMA: mbarriers of the warp's DATA / STAT tiles
+    static constexpr int kWT = WarpThreads<NB, MAD>::value;
+    WarpSmem<NB> w[kWT / 32];
     double scale[NB];
     double offset[NB];
     double rcp[NB + 1];   // 1.0 / m
@@ -276,13 +274,13 @@ __device__ __forceinline__ int count_col(const float (*col)[32], int lane, float
 // below the low bound / strictly below the high bound (positions in the whole column).
 template <int NB, bool UNIT>
 __device__ __noinline__ bool refine_band(const float (*sk)[32], int lane, const float* const* data, long long v,
-                                         const double* scale, const double* offset, int ih, int il, int m,
+                                         const double* scale, const double* offset, int nfiles, int ih, int il, int m,
                                          double sigma, double nlo, double nup, double clo, double cup, double T,
                                          int& lo_in, int& up_in)
 {
     auto bucket = [](float k) { return __float_as_uint(k) & ~idx_mask<NB>(); };
     auto exact_w = [&](float k) {
-        const int i = (int)(__float_as_uint(k) & idx_mask<NB>());
+        const int i = min((int)(__float_as_uint(k) & idx_mask<NB>()), nfiles - 1);
         const double dd = (double)__ldg(data[i] + v);
         return UNIT ? dd : (offset[i] + dd) * scale[i];
     };
@@ -356,12 +354,6 @@ template <int NB, int THREADS> struct WarpBlocks {
     static constexpr int raw = (NB <= 48 ? MB_WARP_BLOCKS : (NB <= 64 ? 4 : (NB <= 96 ? 3 : 2))) * 128 / THREADS;
     static constexpr int value = raw < 1 ? 1 : raw;
 };
-// TMA variant: two staged tiles per warp (2 x NB x 128 bytes) bound the residency, not the registers
-template <int NB, int THREADS> struct TmaBlocks {
-    static constexpr int raw = (NB <= 16 ? 8 : (NB <= 32 ? 6 : (NB <= 48 ? 4 : (NB <= 64 ? 3 : 2)))) * 128 / THREADS;
-    static constexpr int value = raw < 1 ? 1 : raw;
-};
-
 // FULL: every exposure slot is in use (nfiles == NB), so the per-row `i < nfiles` predicates and
 // selects compile away (the common case: depths 4, 8, 12, 16, 24, 32, 48, 64, 96, 128).
 //
@@ -375,21 +367,14 @@ template <int NB, int THREADS> struct TmaBlocks {
 // STRIDED: the rows of the stack are equally spaced in memory (one [N][V] allocation, the layout of the
 // slab slots and of any stacked tensor): row i+1 = row i + S.dstride elements, so an address costs one
 // IMAD.WIDE on the FMA pipe instead of a constant-bank load plus a 64-bit add on the ALU pipe.
-//
-// TMA (needs STRIDED rows with a pitch and base that are multiples of 16 bytes): the [NB][32] DATA and STAT tiles
-// of a warp are fetched by ONE cp.async.bulk.tensor instruction each (2-D tensor map over [row][voxel], box
-// 32 x NB, NaN fill beyond the last voxel) into the warp's shared-memory buffers, a whole tile ahead, completion
-// on an mbarrier.  No load touches a register, no address is computed per row, and pass 1 and the variance
-// pass become short rolled loops over shared memory, so the loop body fits the 32 KB instruction cache.
-template <int NB, bool UNIT, bool FULL, bool MAD = false, bool STRIDED = false, bool TMA = false>
-__global__ void __launch_bounds__((WarpThreads<NB, MAD, TMA>::value),
-                                  (TMA ? TmaBlocks<NB, WarpThreads<NB, MAD, TMA>::value>::value : WarpBlocks<NB, WarpThreads<NB, MAD, TMA>::value>::value))
+template <int NB, bool UNIT, bool FULL, bool MAD = false, bool STRIDED = false>
+__global__ void __launch_bounds__((WarpThreads<NB, MAD>::value), (WarpBlocks<NB, WarpThreads<NB, MAD>::value>::value))
 sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile_begin, const long long tile_end,
-                    const int flags, unsigned long long* slow_total, const __grid_constant__ TmaMaps M)
+                    const int flags, unsigned long long* slow_total)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    BlockSmem<NB, MAD, TMA>& sm = *reinterpret_cast<BlockSmem<NB, MAD, TMA>*>(smem_raw);
-    constexpr int kWT = WarpThreads<NB, MAD, TMA>::value;
+    BlockSmem<NB, MAD>& sm = *reinterpret_cast<BlockSmem<NB, MAD>*>(smem_raw);
+    constexpr int kWT = WarpThreads<NB, MAD>::value;
     constexpr int W = ExpSet<NB>::W;
     constexpr unsigned IDX = (1u << KeyBits<NB>::idx_bits) - 1u;
     // Invalid samples become sentinel keys below every real key (above, for the MAD variant, whose code
@@ -469,27 +454,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
     // (prefetch.global.L1 only reaches L2 on this part -- tools/microbench/l1prefetch.cu: a later load still
     // takes the ~480-cycle L2 latency.  Real L1 fills, cp.async.ca of one word per sector into a dummy
     // shared-memory word, make the later load a 33-cycle L1 hit but measured 10-18 % slower here.)
-    unsigned tma_phase = 0u;
-    constexpr unsigned kTileBytes = NB * 32 * sizeof(float);
-    // one lane requests a tile: both boxes land in the warp's buffers, each completes its own mbarrier
-    auto tma_request = [&](long long t) {
-        mbar_expect_tx(&sm.bar[wib][0], kTileBytes);
-        tma_load_2d(&sm.w[wib].k[0][0], &M.data, (int)(t << 5), 0, &sm.bar[wib][0]);
-        if (want_var) {
-            mbar_expect_tx(&sm.bar[wib][1], kTileBytes);
-            tma_load_2d(&sm.v[TMA ? wib : 0][0][0], &M.stat, (int)(t << 5), 0, &sm.bar[wib][1]);
-        }
-    };
-    if constexpr (TMA) {
-        if (lane == 0) {
-            mbar_init(&sm.bar[wib][0], 1);
-            mbar_init(&sm.bar[wib][1], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (tile0 + wib < ntiles) tma_request(tile0 + wib);
-        }
-        __syncwarp();
-    } else {
+    {
         if (tile0 + wib < ntiles) prefetch_rows(false, tile0 + wib);
         if (want_var && (flags & 16) && tile0 + wib < ntiles) prefetch_rows(true, tile0 + wib);
     }
@@ -503,12 +468,12 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         const long long tile = tile0 + wib;
         const long long v = (tile << 5) + lane;
         const bool act = tile < ntiles && v < A.nvox;
-        if (!TMA && want_var && (flags & 8)) prefetch_rows(true, tile);   // flags & 8: STAT prefetch at tile start (3 % slower)
+        if (want_var && (flags & 8)) prefetch_rows(true, tile);   // flags & 8: STAT prefetch at tile start (3 % slower)
 
         float key[NB];
         ExpSet<NB> inval;
         double sum = 0.0, p = 0.0, T1 = 0.0, S2 = 0.0;
-        if constexpr (!TMA) {
+        {
             // ---- gather: one coalesced load per exposure ------------------------------------------
             // STRIDED: idle lanes (ragged last tile, tiles past the end) re-read the last voxel and are voided
             // after pass 1, so these loads need neither a predicate nor a NaN initialisation per row
@@ -597,57 +562,6 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             T1 = T1c[0]; S2 = S2c[0];
 #pragma unroll
             for (int c = 1; c < NCH; c++) { T1 += T1c[c]; S2 += S2c[c]; }
-        } else {
-            // ---- TMA path: the DATA tile is (or is about to be) in the warp's key column ------------------
-            if (!(tile < ntiles)) continue;                    // no tile, nothing was requested
-            if (lane == 0 && tile + wstride < ntiles) {        // L2 prefetch of the tile after this one
-                tma_prefetch_2d(&M.data, (int)((tile + wstride) << 5), 0);
-                if (want_var) tma_prefetch_2d(&M.stat, (int)((tile + wstride) << 5), 0);
-            }
-            mbar_wait(&sm.bar[wib][0], tma_phase);
-            MB_STAMP(2);
-            // pivot = first valid sample among the first four (tools.c sums are order-sensitive, the pivot is not)
-            bool have_p = false;
-#pragma unroll
-            for (int i = 0; i < 4 && i < NB; i++) {
-                const float d = sk[i][lane];
-                const bool ok = (d == d);
-                const double w = UNIT ? (double)d : (S.os[i].x + (double)d) * S.os[i].y;
-                p = (ok && !have_p) ? w : p;
-                have_p = have_p || ok;
-            }
-            // pass 1 as a rolled loop over the staged rows; the key replaces the sample in place
-#pragma unroll
-            for (int wd = 0; wd < W; wd++) {
-                unsigned bad = 0u;
-                const int hi = (wd + 1) * 32 < NB ? (wd + 1) * 32 : NB;
-#pragma unroll 4
-                for (int i = wd * 32; i < hi; i++) {
-                    const float d = sk[i][lane];
-                    const bool ok = (d == d);
-                    double w;
-                    float kf;
-                    if constexpr (UNIT) {
-                        w = (double)d;
-                        kf = d;
-                    } else {
-                        const double2 os = S.os[i];
-                        w = (os.x + (double)d) * os.y;            // merging.c:426
-                        kf = __double2float_rn(w);
-                    }
-                    double t = w - p;
-                    t = __hiloint2double(ok ? __double2hiint(t) : 0, __double2loint(t));
-                    sum += ok ? w : 0.0;                          // tools.c:13-16, exposure order, no FMA
-                    T1 += t;
-                    S2 = __fma_rn(t, t, S2);
-                    bad |= ok ? 0u : (1u << (i & 31));
-                    const unsigned kb = (__float_as_uint(kf) & keep_mask) | (unsigned)i;
-                    sk[i][lane] = __uint_as_float(ok ? kb : (SENT | (unsigned)i));
-                }
-                inval.w[wd] = bad;
-            }
-#pragma unroll
-            for (int q = 0; q < NB; q++) key[q] = sk[q][lane];
         }
         const int n = NB - inval.count();
         float dspec[2] = {0.f, 0.f};
@@ -661,7 +575,9 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             if (n >= 2 && act) {
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    const int i = (int)(__float_as_uint(key[NB - 1 - j]) & IDX);
+                    // (a key built from a non-finite w is a NaN pattern and the network may leave the canonical NaN in
+                    // this slot: such a voxel is recomputed by the exact path, but its index bits must not address memory)
+                    const int i = min((int)(__float_as_uint(key[NB - 1 - j]) & IDX), nfiles - 1);
                     const float* src;
                     if constexpr (STRIDED) src = S.data[0] + (size_t)i * S.dstride + v;
                     else src = sm.data[i] + v;
@@ -674,7 +590,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         }
         // the STAT rows are prefetched into L1 only now: close enough to their use (after the clip
         // loop) that they are still there, early enough that the latency is covered
-        if (!TMA && want_var && !(flags & (8 | 16)) && !(MB_ABLATE && (flags & 128))) prefetch_rows(true, tile);
+        if (want_var && !(flags & (8 | 16)) && !(MB_ABLATE && (flags & 128))) prefetch_rows(true, tile);
         MB_STAMP(4);   // sort + column store + STAT prefetch
 
 #if !MB_LATE_STAT
@@ -705,7 +621,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
             // exact values in key order (their d re-read through L1 / L2; four lookups in flight)
 #pragma unroll 4
             for (int q = 0; q < n; q++) {
-                const int i = (int)(__float_as_uint(sk[q][lane]) & IDX);
+                const int i = min((int)(__float_as_uint(sk[q][lane]) & IDX), nfiles - 1);   // NaN-pattern keys of non-finite samples
                 const double dd = (double)__ldg(sm.data[i] + v);
                 sw[q][lane] = UNIT ? dd : (sm.offset[i] + dd) * sm.scale[i];
             }
@@ -759,7 +675,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                     b = nb2;
                 }
                 for (int q = 0; q < n; q++)
-                    if (q < a || q >= b) rejected.set_dyn((int)(__float_as_uint(sk[q][lane]) & IDX));
+                    if (q < a || q >= b) rejected.set_dyn(min((int)(__float_as_uint(sk[q][lane]) & IDX), nfiles - 1));
             }
         } else
         if (n >= 2 && !(flags & 4)) {
@@ -830,7 +746,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 }
                 if (lo_band || up_band) {
                     // ~1e-4 of the voxels: settle the band keys from their exact values
-                    if (!refine_band<NB, UNIT>(sk, lane, sm.data, v, sm.scale, sm.offset, ih, il, m, sigma, A.nclip_low,
+                    if (!refine_band<NB, UNIT>(sk, lane, sm.data, v, sm.scale, sm.offset, nfiles, ih, il, m, sigma, A.nclip_low,
                                                A.nclip_up, clo, cup, T, lo_in, up_in)) { slow = true; break; }
                 }
                 lo_in = min(max(lo_in, a), b);
@@ -852,7 +768,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                     for (int j = 0; j < 4; j++) {
                         const int k = k0 + j;
                         const int q = k < r ? (k < r1 ? a + k : nb2 + (k - r1)) : a;
-                        iv[j] = (int)(__float_as_uint(sk[q][lane]) & IDX);
+                        iv[j] = min((int)(__float_as_uint(sk[q][lane]) & IDX), nfiles - 1);
                         const float* src;
                         if constexpr (STRIDED) src = S.data[0] + (size_t)iv[j] * S.dstride + v;
                         else src = sm.data[iv[j]] + v;
@@ -897,42 +813,7 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
         // STAT rows loaded only now (prefetched into L1 after the sort): fewer live registers across the
         // clip loop, more resident blocks per SM.  Two half-batches: the second is in flight while the
         // first is consumed.
-        if constexpr (TMA) {
-            if (want_var) {
-                // the STAT tile arrived long ago (requested with the DATA tile); rolled loop, NACC float32 chains
-                mbar_wait(&sm.bar[wib][1], tma_phase);
-                MB_STAMP(7);   // STAT arrival
-                constexpr int NACC = (NB % 8 == 0) ? 8 : 4;
-                float vacc[NACC];
-#pragma unroll
-                for (int k = 0; k < NACC; k++) vacc[k] = 0.f;
-                const float (*sv)[32] = sm.v[TMA ? wib : 0];
-#pragma unroll
-                for (int wd = 0; wd < W; wd++) {
-                    const unsigned gone = dropped.w[wd];
-                    const int hi = (wd + 1) * 32 < NB ? (wd + 1) * 32 : NB;
-                    for (int i0 = wd * 32; i0 < hi; i0 += NACC) {
-#pragma unroll
-                        for (int j = 0; j < NACC; j++) {
-                            const int i = i0 + j;
-                            const float x = sv[i][lane];
-                            if (!((gone >> (i & 31)) & 1u)) vacc[j] = __fmaf_rn(x, S.scale2f[i], vacc[j]);   // merging.c:431,462
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < NACC; k++) vsum += (double)vacc[k];
-            }
-            // both buffers are free: request the warp's next tile (generic-proxy accesses first made visible
-            // to the async proxy), then flip the parity the next waits will look for
-            __syncwarp();
-            if (lane == 0 && tile + wstride < ntiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                tma_request(tile + wstride);
-            }
-            tma_phase ^= 1u;
-            MB_STAMP(6);   // variance loop + next request
-        } else {
+        {
         float sv[NB];
         if (want_var) {
             const long long vs = act ? v : A.nvox - 1;
@@ -986,6 +867,16 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 if (!dropped.test(i)) vacc[i % NACC] = __fmaf_rn(sv[i], S.scale2f[i], vacc[i % NACC]);
 #pragma unroll
             for (int k = 0; k < NACC; k++) vsum += (double)vacc[k];
+            // the bound needs non-negative terms: a sign bit among the kept STAT samples sends the lane to float64 products
+            unsigned neg = 0u;
+#pragma unroll
+            for (int i = 0; i < NB; i++) neg |= dropped.test(i) ? 0u : __float_as_uint(sv[i]);
+            if (neg & 0x80000000u) {
+                vsum = 0.0;
+#pragma unroll
+                for (int i = 0; i < NB; i++)
+                    if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];   // merging.c:431,462
+            }
             } else
 #endif
             {   // float64 products in exposure order (the MAD variant stays bit-identical to the reference)
@@ -998,9 +889,8 @@ sigclip_warp_kernel(const TileArgs<NB> S, const ClipArgs A, const long long tile
                 if (!dropped.test(i)) vsum += (double)sv[i] * S.scale2[i];
             }
         }
-        }   // !TMA
+        }
 #else
-        static_assert(!TMA, "the TMA variant needs MB_LATE_STAT");
         if (want_var) {
 #pragma unroll
             for (int i = 0; i < NB; i++)

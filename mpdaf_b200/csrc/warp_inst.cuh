@@ -170,8 +170,6 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
     static const bool have_flags = std::getenv("MPDAF_B200_WARP_FLAGS") != nullptr;
     static const int env_flags = have_flags ? std::atoi(std::getenv("MPDAF_B200_WARP_FLAGS")) : 0;
     int flags = have_flags ? env_flags : (NB >= 24 ? 1 : 0);
-    TmaMaps maps;
-    std::memset(&maps, 0, sizeof(maps));
     auto launch = [&](auto kernel, int smem, int kWT) -> int {
         MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
@@ -180,7 +178,7 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
         const long long ntiles = (j.a.nvox + 31) / 32;
         const long long nblocks = (ntiles + (kWT / 32) - 1) / (kWT / 32);
         const int grid = (int)std::max(1LL, std::min(nblocks, (long long)ctx.sm_count * per_sm));
-        kernel<<<grid, kWT, smem, ctx.stream>>>(s, j.a, 0LL, ntiles, flags, ctx.slow, maps);
+        kernel<<<grid, kWT, smem, ctx.stream>>>(s, j.a, 0LL, ntiles, flags, ctx.slow);
         MB_CUDA(cudaGetLastError());
         ctx.launches++;
         return MPDAF_B200_OK;
@@ -188,8 +186,8 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
     if (mad) {   // MAD: one variant per scale mode (row predicates kept: FULL = false)
         constexpr int smem_mad = (int)sizeof(BlockSmem<NB, true>);
         if constexpr (smem_mad <= 227 * 1024) {
-            if (unit) return launch(sigclip_warp_kernel<NB, true, false, true>, smem_mad, WarpThreads<NB, true, false>::value);
-            return launch(sigclip_warp_kernel<NB, false, false, true>, smem_mad, WarpThreads<NB, true, false>::value);
+            if (unit) return launch(sigclip_warp_kernel<NB, true, false, true>, smem_mad, WarpThreads<NB, true>::value);
+            return launch(sigclip_warp_kernel<NB, false, false, true>, smem_mad, WarpThreads<NB, true>::value);
         } else {
             return fail(MPDAF_B200_ERR_ARG, "stack too deep for the MAD warp kernel");
         }
@@ -197,32 +195,13 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
     constexpr int smem = (int)sizeof(BlockSmem<NB>);
     static const bool no_strided = std::getenv("MPDAF_B200_NO_STRIDED") != nullptr;
     const bool strided = full && !no_strided && s.dstride != 0 && (j.a.typ_var != 0 || s.vstride != 0);
-    // TMA variant: equally pitched rows whose base and pitch are multiples of 16 bytes
-    // opt-in (MPDAF_B200_TMA=1): correct and tested, but measured slower than the register gather on B200
-    // (1.37 vs 1.02 ms for 64 planes x 48 exposures: its warps wait on the tile barriers)
-    static const bool no_tma = std::getenv("MPDAF_B200_TMA") == nullptr;
-    if constexpr (NB <= 96) {
-        auto tma_ok = [&](const void* const* rows, unsigned stride) {
-            return stride != 0 && (stride & 3u) == 0 && (reinterpret_cast<uintptr_t>(rows[0]) & 15u) == 0;
-        };
-        const bool need_var = j.a.typ_var == 0;
-        if (strided && !no_tma && j.a.nvox < 0x7FFFFFE0LL && tma_ok(j.data, s.dstride) && (!need_var || tma_ok(j.var, s.vstride)) &&
-            encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, NB, 4ull * s.dstride) &&
-            (!need_var || encode_stack_map(maps.stat, j.var[0], (unsigned long long)j.a.nvox, NB, 4ull * s.vstride))) {
-            constexpr int smem_tma = (int)sizeof(BlockSmem<NB, false, true>);
-            if (!have_flags) flags = 0;   // no phase lock: the loop body fits the instruction cache
-            std::snprintf(ctx.name, ctx.name_len, "sigclip_warp<%d,%s,tma>", NB, unit ? "unit" : "scaled");
-            if (unit) return launch(sigclip_warp_kernel<NB, true, true, false, true, true>, smem_tma, WarpThreads<NB, false, true>::value);
-            return launch(sigclip_warp_kernel<NB, false, true, false, true, true>, smem_tma, WarpThreads<NB, false, true>::value);
-        }
-    }
     if (strided) {
         std::snprintf(ctx.name, ctx.name_len, "sigclip_warp<%d,%s,strided>", NB, unit ? "unit" : "scaled");
-        if (unit) return launch(sigclip_warp_kernel<NB, true, true, false, true>, smem, WarpThreads<NB, false, false>::value);
-        return launch(sigclip_warp_kernel<NB, false, true, false, true>, smem, WarpThreads<NB, false, false>::value);
+        if (unit) return launch(sigclip_warp_kernel<NB, true, true, false, true>, smem, WarpThreads<NB, false>::value);
+        return launch(sigclip_warp_kernel<NB, false, true, false, true>, smem, WarpThreads<NB, false>::value);
     }
-    if (unit) return full ? launch(sigclip_warp_kernel<NB, true, true>, smem, WarpThreads<NB, false, false>::value) : launch(sigclip_warp_kernel<NB, true, false>, smem, WarpThreads<NB, false, false>::value);
-    return full ? launch(sigclip_warp_kernel<NB, false, true>, smem, WarpThreads<NB, false, false>::value) : launch(sigclip_warp_kernel<NB, false, false>, smem, WarpThreads<NB, false, false>::value);
+    if (unit) return full ? launch(sigclip_warp_kernel<NB, true, true>, smem, WarpThreads<NB, false>::value) : launch(sigclip_warp_kernel<NB, true, false>, smem, WarpThreads<NB, false>::value);
+    return full ? launch(sigclip_warp_kernel<NB, false, true>, smem, WarpThreads<NB, false>::value) : launch(sigclip_warp_kernel<NB, false, false>, smem, WarpThreads<NB, false>::value);
 }
 
 template <int NB>

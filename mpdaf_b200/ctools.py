@@ -21,6 +21,7 @@ LIBRARY_PATH = os.path.dirname(os.path.abspath(__file__))
 # element types / locations / return codes (include/mpdaf_b200.h)
 F32, F64 = 4, 8
 HOST, DEVICE = 0, 1
+ALL_DEVICES = -1   # `device` of a HOST-location call: spread the wavelength slabs over the configured devices
 OK, ERR_ARG, ERR_CUDA, ERR_IO, ERR_SHAPE = 0, 1, 2, 3, 4
 
 try:
@@ -93,6 +94,10 @@ else:
     ctools.mpdaf_b200_slow_voxels.argtypes = [ctypes.c_int, ctypes.c_int]
     ctools.mpdaf_b200_device_count.restype = ctypes.c_int
     ctools.mpdaf_b200_device_count.argtypes = []
+    ctools.mpdaf_b200_set_devices.restype = ctypes.c_int
+    ctools.mpdaf_b200_set_devices.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    ctools.mpdaf_b200_release.restype = ctypes.c_int
+    ctools.mpdaf_b200_release.argtypes = []
     ctools.mpdaf_b200_fits_image_info.restype = ctypes.c_int
     ctools.mpdaf_b200_fits_image_info.argtypes = [
         ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_long * 3),

@@ -165,6 +165,19 @@ def _silenced(fn, *args):
         os.close(devnull)
 
 
+_omp_team = None
+
+
+def set_ref_threads(n):
+    """Default OpenMP team size for the reference's next parallel regions (`omp_set_num_threads` of the libgomp the
+    reference build links): launchers such as torchrun export OMP_NUM_THREADS=1, and tests on a few planes need fewer
+    threads than planes (the reference double-counts its counters otherwise, merging.c:129-132)."""
+    global _omp_team
+    import ctypes
+    ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    _omp_team = int(n)
+
+
 def ref_threads(nfiles, typ_var, omp_threads=None):
     """Effective team size of the reference (merging.c:58-90)."""
     import resource
@@ -173,7 +186,7 @@ def ref_threads(nfiles, typ_var, omp_threads=None):
     t = min(t, 1000 // nfiles)
     if typ_var == 0:
         t //= 2
-    omp = omp_threads or int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
+    omp = omp_threads or _omp_team or int(os.environ.get("OMP_NUM_THREADS", os.cpu_count()))
     return max(1, min(t, omp))
 
 

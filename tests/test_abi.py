@@ -169,7 +169,9 @@ def test_no_cpu_fallback_without_gpu(tmp_path):
     rc = ctools.mpdaf_merging_median(buf, out, expmap, valid)
     assert rc == ERR_CUDA
     assert buf.value == "\n".join(files).encode()          # the name list is never mutated
-    assert (out == -1).all() and (valid == 0).all()        # nothing was written
+    # a failed call never leaves caller-allocated buffers half written (the reference's caller ignores the return
+    # value, cubelist.py:456): NaN cube, empty exposure map, untouched counters
+    assert np.isnan(out).all() and (expmap == 0).all() and (valid == 0).all()
     from mpdaf_b200 import CubeList
     from mpdaf_b200.ctools import CtoolsError
     with pytest.raises(CtoolsError):
@@ -184,3 +186,82 @@ def test_shape_mismatch_is_an_error(tmp_path):
     valid = np.zeros(2, dtype=np.intc)
     rc = ctools.mpdaf_merging_median(ctypes.create_string_buffer((a[0] + "\n" + b[0]).encode()), out, expmap, valid)
     assert rc == ERR_SHAPE                                 # merging.c:195-199
+    assert np.isnan(out).all() and (expmap == 0).all()     # outputs of the failed call are filled, not left as they were
+
+
+def _patch_card(path, key, card_text):
+    """Overwrite (or append before END) one 80-character card of the DATA extension's header."""
+    raw = bytearray(open(path, "rb").read())
+    pos = raw.find(b"EXTNAME = 'DATA")
+    assert pos > 0
+    start = pos - pos % 2880
+    end = raw.find(b"END" + b" " * 77, start)
+    card = card_text.ljust(80).encode()
+    k = raw.find(key.ljust(8).encode() + b"=", start, end)
+    if k < 0:
+        # replace the END card and put END in the next slot (the header block has room in these small files)
+        raw[end:end + 80] = card
+        raw[end + 80:end + 160] = b"END".ljust(80)
+    else:
+        raw[k:k + 80] = card
+    open(path, "wb").write(bytes(raw))
+
+
+def test_fits_header_hardening(tmp_path):
+    """Malformed or unsupported headers are refused with an error code, never indexed out of bounds
+    (fits_reader.cpp: NAXIS0 / NAXIS9 cards, BSCALE / BZERO, which cfitsio would apply while reading)."""
+    cube = [np.arange(12, dtype=np.float32).reshape(3, 2, 2)]
+    naxes = (ctypes.c_long * 3)()
+    bitpix = ctypes.c_int()
+    off = ctypes.c_longlong()
+    for key, text, ok in (("NAXIS9", "NAXIS9  =                   77", True), ("NAXIS0", "NAXIS0  =                   77", True),
+                          ("BSCALE", "BSCALE  =                  2.0", False), ("BZERO", "BZERO   =                 10.0", False),
+                          ("BSCALE", "BSCALE  =                  1.0", True)):
+        f = write_exposures(tmp_path, cube, prefix="h" + key + str(ok))[0]
+        _patch_card(f, key, text)
+        rc = ctools.mpdaf_b200_fits_image_info(f.encode(), b"DATA", ctypes.byref(naxes), ctypes.byref(bitpix), ctypes.byref(off))
+        assert (rc == 0) == ok, (key, text, rc)
+        if ok:
+            assert tuple(naxes) == (2, 2, 3) and bitpix.value == -32
+
+
+REF_LOADER = "/root/reference/lib/mpdaf/tools/ctools.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LOADER), reason="the reference tree is not present on this machine")
+def test_library_binds_through_the_reference_loader(tmp_path):
+    """Drop-in boundary: the reference's UNMODIFIED lib/mpdaf/tools/ctools.py (loaded from where it lies, never
+    copied into the repository) finds `_ctools.so` beside itself, binds both merging symbols with its own argtypes
+    and gets a clean error code and filled outputs on a machine without a B200 (ctools.py:52-92, cubelist.py:456)."""
+    import importlib.util
+    import shutil
+    import subprocess
+    import sys
+    work = tmp_path / "tools"
+    work.mkdir()
+    shutil.copy(REF_LOADER, work / "ctools.py")            # temp dir only: the loader looks for _ctools next to itself
+    os.symlink(os.path.join(ROOT, "mpdaf_b200", "_ctools.so"), work / "_ctools.so")
+    data = [np.full((3, 2, 2), v, dtype=np.float32) for v in (1.0, 2.0, 6.0)]
+    files = write_exposures(tmp_path, data, data)
+    code = f"""
+import sys, importlib.util, numpy as np, ctypes
+spec = importlib.util.spec_from_file_location('refctools', r'{work / "ctools.py"}')
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+lib = m.ctools
+n, nv = 3, 12
+files = {files!r}
+data, var = np.empty(nv), np.empty(nv)
+expmap = np.empty(nv, dtype=np.int32)
+sel, val = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+rc = lib.mpdaf_merging_sigma_clipping(ctypes.c_char_p('\\n'.join(files).encode('utf8')), data, var, expmap,
+                                      np.ones(n), np.zeros(n), sel, val, 2, 5.0, 5.0, 2, 0, 0)
+rc2 = lib.mpdaf_merging_median(ctypes.c_char_p('\\n'.join(files).encode('utf8')), data, expmap, val)
+print('RC', rc, rc2, int(np.isnan(data).all()), int((expmap == 0).all()), int(np.isnan(var).all()))
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("RC")][0].split()
+    if ctools.mpdaf_b200_device_count() == 0:
+        assert line[1:] == [str(ERR_CUDA), str(ERR_CUDA), "1", "1", "1"]
+    else:
+        assert line[1:3] == ["0", "0"]
