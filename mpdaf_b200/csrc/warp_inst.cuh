@@ -91,6 +91,9 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
         const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;   // read per call: tests switch kernel families
         const bool need_var = j.a.typ_var == 0;
         if (off || j.a.mad || j.median || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL) return MPDAF_B200_OK;
+        // 49 .. 64 exposures with var = 'propagate': nine consumer warps and 128 unsorted-key registers leave the pair
+        // kernel behind the warp kernel (2290 vs 2580 GB/s at N = 64, profiles/r02_depth_sweep.txt); it still wins without STAT
+        if (NB > 48 && need_var && std::getenv("MPDAF_B200_PAIR_ALWAYS") == nullptr) return MPDAF_B200_OK;
         auto pitch_of = [&](const void* const* rows) -> unsigned long long {   // elements between rows, 0 = not equally pitched / unaligned
             if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
             if (j.nfiles == 1) return (unsigned long long)((j.a.nvox + 3) / 4 * 4);

@@ -110,6 +110,22 @@ def test_pair_kernel_means_within_1e_12(scaled):
             np.testing.assert_allclose(got["var"], want["var"], rtol=3e-7, atol=0, equal_nan=True)   # float32 chains of 3
 
 
+def test_pair_kernel_deep_bucket_with_stat(monkeypatch):
+    """49 .. 64 exposures with var = 'propagate' normally go to the warp kernel (faster there); the pair kernel's
+    instantiation stays correct and is kept covered through MPDAF_B200_PAIR_ALWAYS."""
+    monkeypatch.setenv("MPDAF_B200_PAIR_ALWAYS", "1")
+    rng = np.random.default_rng(64)
+    for n in (49, 64):
+        data, var = random_stack(rng, n, (4, 9, 10), nan_frac=0.1, outlier_frac=0.05)
+        kw = dict(scales=np.linspace(0.8, 1.3, n), offsets=np.linspace(-1, 1, n), nclip=2.5, vartype="propagate")
+        got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
+        assert "sigclip_pair<64" in cuda().kernel_name()
+        assert_same_result(got, oracle.combine_port(data, var, **kw))
+    monkeypatch.delenv("MPDAF_B200_PAIR_ALWAYS")
+    got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
+    assert "sigclip_warp<64" in cuda().kernel_name()
+
+
 @pytest.mark.parametrize("nmax,lo,up,nstop", [(0, 2.0, 2.0, 2), (1, 1.5, 3.0, 1), (3, 1.0, 1.0, 3),
                                               (2, 3.0, 1.5, 5), (5, 1.2, 1.2, 2), (2, 0.5, 0.5, 1),
                                               (2, 5.0, 5.0, 0), (10, 1.0, 2.0, 2)])
@@ -602,3 +618,36 @@ def test_release_frees_and_the_next_call_allocates_again():
     assert free1 > free0                                   # the staging slots went back to the driver
     assert_same_result(cuda().combine_cuda(data, var, nclip=3.0, location="host"), want)
     assert_same_result(cuda().combine_cuda(data, var, nclip=3.0, location="device_pitched"), want)
+
+
+def test_outputs_stay_inside_their_buffers(family):
+    """Canary margins around every output of a DEVICE-location call (compute-sanitizer is closed on this pool): ragged
+    voxel counts (not a multiple of the 64-voxel tile, odd, tiny) must leave the words before and after untouched."""
+    import torch
+    from mpdaf_b200.ctools import DEVICE, check, ctools
+    from mpdaf_b200.cubelist import _ptr_table
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(99)
+    n = 12
+    for nvox in (1, 63, 65, 127, 1001, 4097):
+        pitch = (nvox + 31) // 32 * 32
+        d = torch.full((n, pitch), float("nan"), dtype=torch.float32, device=dev)
+        v = torch.full((n, pitch), float("nan"), dtype=torch.float32, device=dev)
+        d[:, :nvox] = torch.from_numpy((10 + rng.standard_normal((n, nvox))).astype(np.float32)).to(dev)
+        v[:, :nvox] = 1.0
+        pad = 64
+        out = torch.full((nvox + 2 * pad,), -7.0, dtype=torch.float64, device=dev)
+        outvar = torch.full((nvox + 2 * pad,), -7.0, dtype=torch.float64, device=dev)
+        expmap = torch.full((nvox + 2 * pad,), -7, dtype=torch.int32, device=dev)
+        kd, dptr = _ptr_table([d[i].data_ptr() for i in range(n)])
+        kv, vptr = _ptr_table([v[i].data_ptr() for i in range(n)])
+        valid, select = np.zeros(n, dtype=np.intc), np.zeros(n, dtype=np.intc)
+        rc = ctools.mpdaf_b200_sigma_clipping_arrays(n, dptr, vptr, 4, nvox, DEVICE, 0, out[pad:].data_ptr(), outvar[pad:].data_ptr(),
+                                                     expmap[pad:].data_ptr(), None, None, select, valid, 2, 3.0, 3.0, 2, 0, 0,
+                                                     torch.cuda.current_stream(dev).cuda_stream)
+        check(rc, "canary run")
+        torch.cuda.synchronize()
+        for t in (out, outvar, expmap):
+            assert bool((t[:pad] == -7).all()) and bool((t[pad + nvox:] == -7).all()), (nvox, cuda().kernel_name())
+            assert not bool((t[pad:pad + nvox] == -7).any())
+        assert (valid == nvox).all()
