@@ -12,6 +12,7 @@
 #include "launch.h"
 #include "sigclip_warp.cuh"
 #include "sigclip_pair.cuh"
+#include "median_pipe.cuh"
 
 namespace mb {
 
@@ -210,6 +211,38 @@ int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
 template <int NB>
 int launch_median_warp_impl(const Job& j, LaunchCtx& ctx)
 {
+    // TMA-pipelined kernel (median_pipe.cuh) when the rows are equally pitched and 16-byte aligned: 8 .. 48 exposures
+    // (profiles/r02_depth_sweep.txt: 4650 / 5530 / 5430 / 5270 / 5530 / 4070 GB/s at N = 8 / 12 / 16 / 24 / 32 / 48 against
+    // 4210 / 4500 / 4440 / 4300 / 3990 / 3340 of the register-gather kernel, which stays ahead at N = 4 and from N = 64 on)
+    if constexpr (NB >= 8 && NB <= 48) {
+        const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;
+        auto pitch_of = [&](const void* const* rows) -> unsigned long long {
+            if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
+            if (j.nfiles == 1) return (unsigned long long)((j.a.nvox + 3) / 4 * 4);
+            const long long step = static_cast<const char*>(rows[1]) - static_cast<const char*>(rows[0]);
+            if (step < j.a.nvox * 4 || (step & 15) != 0) return 0ull;
+            for (int i = 2; i < j.nfiles; i++)
+                if (static_cast<const char*>(rows[i]) - static_cast<const char*>(rows[i - 1]) != step) return 0ull;
+            return (unsigned long long)(step >> 2);
+        };
+        const unsigned long long dp = off ? 0ull : pitch_of(j.data);
+        TmaMaps maps;
+        std::memset(&maps, 0, sizeof(maps));
+        if (dp != 0 && j.a.nvox >= 1 && j.a.nvox < 0x7FFFFF00LL && !(reinterpret_cast<uintptr_t>(j.a.out) & 15u) &&
+            !(reinterpret_cast<uintptr_t>(j.a.expmap) & 7u) &&
+            encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * dp, (unsigned)MedianPipeCfg<NB>::TV, NB, true)) {
+            using Cfg = MedianPipeCfg<NB>;
+            std::snprintf(ctx.name, ctx.name_len, "median_pipe<%d>", NB);
+            const int smem = (int)sizeof(MedianPipeSmem<NB>);
+            MB_CUDA(cudaFuncSetAttribute(median_pipe_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const long long ntiles = (j.a.nvox + Cfg::TV - 1) / Cfg::TV;
+            const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
+            median_pipe_kernel<NB><<<grid, Cfg::threads, smem, ctx.stream>>>(j.a, ntiles, maps);
+            MB_CUDA(cudaGetLastError());
+            ctx.launches++;
+            return MPDAF_B200_OK;
+        }
+    }
     TileArgs<NB> s;
     fill_tile_args(s, j);
     const bool full = (j.nfiles == NB);
