@@ -135,6 +135,12 @@ const char *mpdaf_b200_last_kernel_name(void);
  * CubeList._compute_expnb (cubelist.py:69-74), obtained on the device instead of a host pass. */
 int mpdaf_b200_last_expmap_histogram(long long *hist, int nbins);
 
+/* Finite mask of a DEVICE-resident output cube: mask[i] = 1 where data[i] is NaN or infinite, else 0 (one byte per
+ * voxel, device memory of `device`), and the number of masked voxels.  What the reference computes on the host when
+ * it wraps the combined arrays in a Cube (lib/mpdaf/obj/cubelist.py:399-400). */
+int mpdaf_b200_finite_mask(const double *data, long long nvox, int device, unsigned char *mask,
+                           long long *nmasked, void *stream);
+
 /* Diagnostic: voxels that the certified fast path handed to the exact per-voxel fallback
  * on `device` since the last reset (see DESIGN.md "certified decisions"); -1 if unknown. */
 long long mpdaf_b200_slow_voxels(int device, int reset);

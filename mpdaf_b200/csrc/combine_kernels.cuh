@@ -279,6 +279,31 @@ static __global__ void expmap_hist_kernel(const int* __restrict__ expmap, long l
         if (s_hist[i]) atomicAdd(hist + i, (unsigned long long)s_hist[i]);
 }
 
+// Mask of the voxels that hold no finite value (what the reference builds on the host when it wraps the combined
+// arrays in a Cube, lib/mpdaf/obj/cubelist.py:399-400 -> data.py mask = ~isfinite): one byte per voxel, 1 = masked.
+// `var` may be null; when given, a voxel with a non-finite variance is NOT masked (the reference masks on data only).
+static __global__ void finite_mask_kernel(const double* __restrict__ data, long long n, unsigned char* __restrict__ mask,
+                                          unsigned long long* __restrict__ nmasked)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    unsigned local = 0;
+    for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        unsigned packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const long long j = i + k;
+            const unsigned long long bits = j < n ? (unsigned long long)__double_as_longlong(__ldcs(data + j)) : 0ull;
+            const unsigned bad = ((bits >> 52) & 0x7FFull) == 0x7FFull ? 1u : 0u;   // exponent all ones: inf or NaN
+            packed |= bad << (8 * k);
+            local += bad;
+        }
+        if (i + 3 < n && (reinterpret_cast<uintptr_t>(mask + i) & 3u) == 0) *reinterpret_cast<unsigned*>(mask + i) = packed;
+        else for (int k = 0; k < 4 && i + k < n; k++) mask[i + k] = (unsigned char)((packed >> (8 * k)) & 1u);
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local && nmasked) atomicAdd(nmasked, (unsigned long long)local);
+}
+
 // In-place byte swap of big-endian float32 samples staged from a FITS HDU.
 static __global__ void bswap32_kernel(uint32_t* __restrict__ p, long long n)
 {

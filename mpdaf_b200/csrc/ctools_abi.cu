@@ -1011,6 +1011,31 @@ int mpdaf_b200_release(void)
     return MPDAF_B200_OK;
 }
 
+// Finite mask of a device-resident output cube: mask[i] = 1 where data[i] is NaN or infinite.
+int mpdaf_b200_finite_mask(const double* data, long long nvox, int device, unsigned char* mask, long long* nmasked, void* stream)
+{
+    if ((!data || !mask) && nvox > 0) return fail(MPDAF_B200_ERR_ARG, "null argument");
+    if (nvox < 0) return fail(MPDAF_B200_ERR_ARG, "bad voxel count");
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    DeviceGuard guard;
+    const int rc = device_ready(device);
+    if (rc != MPDAF_B200_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DeviceState& d = g_dev[device];
+    unsigned long long* counter = d.hist;                                   // first histogram bin doubles as the counter
+    MB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    if (nvox > 0) {
+        const int grid = (int)std::min<long long>((nvox / 4 + 255) / 256 + 1, (long long)d.sm_count * 16);
+        finite_mask_kernel<<<grid, 256, 0, st>>>(data, nvox, mask, counter);
+        MB_CUDA(cudaGetLastError());
+    }
+    unsigned long long host = 0;
+    MB_CUDA(cudaMemcpyAsync(&host, counter, sizeof host, cudaMemcpyDeviceToHost, st));
+    MB_CUDA(cudaStreamSynchronize(st));
+    if (nmasked) *nmasked = (long long)host;
+    return MPDAF_B200_OK;
+}
+
 double mpdaf_b200_last_kernel_ms(void) { return g_last_kernel_ms; }
 
 int mpdaf_b200_last_expmap_histogram(long long* hist, int nbins)

@@ -139,7 +139,7 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             MB_CUDA(cudaMemsetAsync(ctx.slow_n, 0, sizeof(unsigned), ctx.stream));
             const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
-            static const int pair_flags = std::getenv("MPDAF_B200_PAIR_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_PAIR_FLAGS")) : 1;
+            static const int pair_flags = std::getenv("MPDAF_B200_PAIR_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_PAIR_FLAGS")) : 2;
             kernel<<<grid, Cfg::threads, smem, ctx.stream>>>(s, j.a, ntiles, ctx.slow_q, ctx.slow_n, ctx.slow_cap, pair_flags, maps);
             MB_CUDA(cudaGetLastError());
             // queued voxels (uncertifiable from their keys): the reference algorithm restated literally, one thread each

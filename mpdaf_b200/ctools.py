@@ -98,6 +98,9 @@ else:
     ctools.mpdaf_b200_set_devices.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     ctools.mpdaf_b200_release.restype = ctypes.c_int
     ctools.mpdaf_b200_release.argtypes = []
+    ctools.mpdaf_b200_finite_mask.restype = ctypes.c_int
+    ctools.mpdaf_b200_finite_mask.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
+                                              ctypes.POINTER(ctypes.c_longlong), ctypes.c_void_p]
     ctools.mpdaf_b200_fits_image_info.restype = ctypes.c_int
     ctools.mpdaf_b200_fits_image_info.argtypes = [
         ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_long * 3),

@@ -91,7 +91,8 @@ class Cube:
     """Combined cube: `data` (nz, ny, nx), optional `var`, two header dicts."""
 
     def __init__(self, data, var=None, primary_header=None, data_header=None, unit=None,
-                 filename=None, comments=()):
+                 filename=None, comments=(), mask=None):
+        self._mask = mask
         self.data = data
         self.var = var
         self.primary_header = dict(primary_header or {})
@@ -106,7 +107,10 @@ class Cube:
 
     @property
     def mask(self):
-        """True where the voxel holds no finite value (reference Cube masks ~isfinite)."""
+        """True where the voxel holds no finite value (reference Cube masks ~isfinite).  Device-resident
+        combinations bring the mask with them (built on the device, `mpdaf_b200_finite_mask`)."""
+        if self._mask is not None:
+            return self._mask
         return ~np.isfinite(self.data)
 
     def write(self, filename, dtype=np.float32):
@@ -353,6 +357,9 @@ class CubeList:
                       method='obj.cubelist.median', header=header)
         expmap = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
         cube = self.save_combined_cube(data, **kwargs)
+        cube._mask = self.__dict__.pop('_device_mask', None)
+        if cube._mask is not None:
+            cube._mask = cube._mask.reshape(cube.data.shape)
         return cube, expmap, stat_pix
 
     def combine(self, nmax=2, nclip=5.0, nstop=2, var='propagate', mad=False, header=None):
@@ -431,52 +438,104 @@ class CubeList:
                       method='obj.cubelist.merging')
         expmap = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
         cube = self.save_combined_cube(data, var=vardata, **kwargs)
+        cube._mask = self.__dict__.pop('_device_mask', None)
+        if cube._mask is not None:
+            cube._mask = cube._mask.reshape(cube.data.shape)
         return cube, expmap, statpix
 
     # ------------------------------------------------------------------
     # The reference's "py" route (cubelist.py:77-216, :538-576; merging.pyx:61-125): same statistics,
     # optional per-cube (y, x) placement inside a larger output grid, and a `rejmap` output.  Here it
     # is the same CUDA path fed with NaN-padded exposures; `rejmap` = valid samples - expmap.
-    def _placed_exposures(self, extname, nl, pos, shapes):
+    def _placed_planes(self, images, z0, z1, pos, shapes):
+        """Planes [z0, z1) of every exposure on the output grid (NaN outside an exposure's footprint)."""
         nz, ny, nx = self.shape
-        nl = nz if nl is None else int(nl)
         out = []
-        for i, f in enumerate(self.files):
-            img = _fits.read_image(f, extname)
+        for i, img in enumerate(images):
             if pos is None and img.shape[1:] == (ny, nx):
-                out.append(np.ascontiguousarray(img[:nl], dtype=np.float32))
+                out.append(np.ascontiguousarray(img[z0:z1], dtype=np.float32))
                 continue
-            arr = np.full((nl, ny, nx), np.nan, dtype=np.float32)
+            arr = np.full((z1 - z0, ny, nx), np.nan, dtype=np.float32)
             y0, x0 = (0, 0) if pos is None else (int(pos[i][0]), int(pos[i][1]))
             sy, sx = img.shape[1:] if shapes is None else (int(shapes[i][0]), int(shapes[i][1]))
             ys, xs = max(y0, 0), max(x0, 0)
             ye, xe = min(y0 + sy, ny), min(x0 + sx, nx)
             if ye > ys and xe > xs:
-                arr[:, ys:ye, xs:xe] = img[:nl, ys - y0:ye - y0, xs - x0:xe - x0]
+                arr[:, ys:ye, xs:xe] = img[z0:z1, ys - y0:ye - y0, xs - x0:xe - x0]
             out.append(arr)
-        return out, nl
+        return out
 
     def _pycombine(self, nmax=2, nclip=5.0, var='propagate', nstop=2, nl=None, header=None, mad=False,
                    pos=None, shapes=None, method='obj.cubelist.pycombine'):
-        data, nl = self._placed_exposures('DATA', nl, pos, shapes)
-        stat = self._placed_exposures('STAT', nl, pos, shapes)[0] if var == 'propagate' else None
-        shape = (nl,) + tuple(self.shape[1:])
-        inner = CubeList.from_arrays(data, stat, scalelist=self.flux_scales, offsetlist=self.flux_offsets,
-                                     names=self.files)
-        inner._headers = self._headers
-        inner.unit = self.unit
-        cube, expmap, stat_pix = inner.combine(nmax=nmax, nclip=nclip, nstop=nstop, var=var, mad=mad, header=header)
-        nvalid = np.zeros(shape, dtype=np.int32)
-        for d in data:
-            nvalid += ~np.isnan(d)
-        rejmap_data = (nvalid - expmap.data).astype(np.int32)
-        for c in (cube, expmap):
-            for key in list(c.primary_header):
-                if key.startswith('HIERARCH MPDAF METH') and key.endswith(' ID'):
-                    c.primary_header[key] = (method, 'MPDAF method identifier')
-        rejmap = Cube(rejmap_data, primary_header=expmap.primary_header, data_header=expmap.data_header,
-                      unit='dimensionless', comments=expmap.comments)
-        return cube, expmap, stat_pix, rejmap
+        """The reference's "py" route (cubelist.py:77-216): like the reference, which walks the cubes plane by plane
+        (cubelist.py:141-152), the exposures are placed on the output grid a few wavelength planes at a time -- host
+        memory stays bounded (MPDAF_B200_PYCOMBINE_BYTES, default 1 GiB of placed samples) however large the mosaic
+        -- and every chunk goes through the same CUDA path; the counters accumulate over the chunks."""
+        import os
+        from .ctools import ctools, check, HOST
+        if var not in ('propagate', 'stat_mean', 'stat_one'):
+            raise ValueError("var must be 'propagate', 'stat_mean' or 'stat_one'")
+        var_mean = {'propagate': 0, 'stat_mean': 1, 'stat_one': 2}[var]
+        nclip_low, nclip_up = (nclip, nclip) if np.isscalar(nclip) else nclip
+        nz, ny, nx = self.shape
+        nl = nz if nl is None else int(nl)
+        n = self.nfiles
+        plane = ny * nx
+        images = [_fits.read_image(f, 'DATA') for f in self.files]
+        stats = [_fits.read_image(f, 'STAT') for f in self.files] if var_mean == 0 else None
+        budget = int(os.environ.get('MPDAF_B200_PYCOMBINE_BYTES', 1 << 30))
+        step = max(1, min(nl, budget // max(1, n * plane * 4 * (2 if var_mean == 0 else 1))))
+        data = np.empty(nl * plane, dtype=np.float64)
+        vardata = np.empty(nl * plane, dtype=np.float64)
+        expmap = np.empty(nl * plane, dtype=np.int32)
+        rejmap_data = np.empty((nl, ny, nx), dtype=np.int32)
+        valid_pix = np.zeros(n, dtype=np.int32)
+        select_pix = np.zeros(n, dtype=np.int32)
+        scale = np.ascontiguousarray(self.flux_scales if self.flux_scales is not None else np.ones(n), dtype=np.float64)
+        offset = np.ascontiguousarray(self.flux_offsets if self.flux_offsets is not None else np.zeros(n), dtype=np.float64)
+        hist = np.zeros(n + 1, dtype=np.int64)
+        part = np.zeros(n + 1, dtype=np.int64)
+        for z0 in range(0, nl, step):
+            z1 = min(nl, z0 + step)
+            d = self._placed_planes(images, z0, z1, pos, shapes)
+            v = self._placed_planes(stats, z0, z1, pos, shapes) if stats is not None else None
+            keep_d, dptr = _ptr_table([a.ctypes.data for a in d])
+            keep_v, vptr = (None, None) if v is None else _ptr_table([a.ctypes.data for a in v])
+            sl = slice(z0 * plane, z1 * plane)
+            rc = ctools.mpdaf_b200_sigma_clipping_arrays(
+                n, dptr, vptr, 4, (z1 - z0) * plane, HOST, 0, data[sl].ctypes.data, vardata[sl].ctypes.data,
+                expmap[sl].ctypes.data, scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix,
+                int(nmax), float(nclip_low), float(nclip_up), int(nstop), int(var_mean), int(mad), None)
+            check(rc, 'mpdaf_b200_sigma_clipping_arrays')
+            if ctools.mpdaf_b200_last_expmap_histogram(part, n + 1) == 0:
+                hist += part
+            nvalid = np.zeros((z1 - z0, ny, nx), dtype=np.int32)
+            for a in d:
+                nvalid += ~np.isnan(a)
+            rejmap_data[z0:z1] = nvalid - expmap[sl].reshape(z1 - z0, ny, nx)     # merging.pyx:110
+        shape = (nl, ny, nx)
+        data, vardata, expmap = data.reshape(shape), vardata.reshape(shape), expmap.reshape(shape)
+        npixels = nl * plane
+        statpix = StatTable([self.files, npixels - valid_pix, valid_pix - select_pix],
+                            names=['FILENAME', 'NPIX_NAN', 'NPIX_REJECTED'])
+        # provenance keywords of the reference's pycombine (cubelist.py:199-205)
+        keywords = [('nmax', nmax, 'max number of clipping iterations'),
+                    ('nclip_low', nclip_low, 'lower clipping parameter'),
+                    ('nclip_up', nclip_up, 'upper clipping parameter'),
+                    ('var', var, 'type of variance'),
+                    ('mad', bool(mad), 'use of MAD')]
+        expnb = int(np.argmax(hist[1:]) + 1) if hist[1:].any() else 0
+        saved_shape = self.shape
+        self.shape = shape
+        try:
+            kwargs = dict(expnb=expnb, keywords=keywords, header=header, method=method)
+            expmap_cube = self.save_combined_cube(expmap, unit='dimensionless', **kwargs)
+            cube = self.save_combined_cube(data, var=vardata, **kwargs)
+        finally:
+            self.shape = saved_shape
+        rejmap = Cube(rejmap_data, primary_header=expmap_cube.primary_header, data_header=expmap_cube.data_header,
+                      unit='dimensionless', comments=expmap_cube.comments)
+        return cube, expmap_cube, statpix, rejmap
 
     def pycombine(self, nmax=2, nclip=5.0, var='propagate', nstop=2, nl=None, header=None, mad=False):
         """`CubeList.combine` with the reference's pycombine signature and 4-tuple return
@@ -505,6 +564,7 @@ class CubeList:
                 self.nfiles, dptr, st.elem_type, npixels, DEVICE, st.device,
                 out.data_ptr(), expmap.data_ptr(), valid_pix, stream)
             check(rc, 'mpdaf_b200_median_arrays')
+            self._device_mask = self._finite_mask_on_device(out, npixels, st.device, stream)
             return out.cpu().numpy(), None, expmap.cpu().numpy()
         outvar = torch.empty(npixels, dtype=torch.float64, device=dev)
         keep_v, vptr = (None, None) if st.var_ptrs is None else _ptr_table(st.var_ptrs)
@@ -513,7 +573,19 @@ class CubeList:
             out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(),
             scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix, *params, stream)
         check(rc, 'mpdaf_b200_sigma_clipping_arrays')
+        self._device_mask = self._finite_mask_on_device(out, npixels, st.device, stream)
         return out.cpu().numpy(), outvar.cpu().numpy(), expmap.cpu().numpy()
+
+    @staticmethod
+    def _finite_mask_on_device(out, npixels, device, stream):
+        """~isfinite of the combined cube, computed where the cube lies."""
+        import torch
+        from .ctools import ctools, check
+        mask = torch.empty(max(npixels, 1), dtype=torch.uint8, device=out.device)
+        nmasked = ctypes.c_longlong(0)
+        rc = ctools.mpdaf_b200_finite_mask(out.data_ptr(), npixels, device, mask.data_ptr(), ctypes.byref(nmasked), stream)
+        check(rc, 'mpdaf_b200_finite_mask')
+        return mask[:npixels].cpu().numpy().astype(bool)
 
 
 class CubeMosaic(CubeList):

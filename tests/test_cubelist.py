@@ -202,3 +202,125 @@ def test_expnb_histogram_on_device():
     assert_array_equal(hist, np.bincount(expmap.data.ravel(), minlength=8))
     cube, expmap, _ = clist.median()
     assert _expnb_from_device(7) == _compute_expnb(expmap.data)
+
+
+def _fits_standard_check(path):
+    """Independent check of a written file against the FITS 4.0 standard -- written from the standard, not from
+    mpdaf_b200/fits.py: 2880-byte blocks, 80-character ASCII cards, mandatory keywords in order, END card, data
+    size |BITPIX| / 8 * prod(NAXISn) padded to a block, big-endian IEEE floats.  Returns {extname: array}."""
+    raw = open(path, 'rb').read()
+    assert len(raw) % 2880 == 0, 'file is not a whole number of 2880-byte blocks'
+    pos, hdus, first = 0, {}, True
+    while pos < len(raw):
+        cards, done = [], False
+        while not done:
+            block = raw[pos:pos + 2880]
+            assert len(block) == 2880
+            pos += 2880
+            for c in range(36):
+                card = block[80 * c:80 * c + 80]
+                assert all(32 <= b < 127 for b in card), 'header holds a non-printable byte'
+                text = card.decode('ascii')
+                if text.startswith('END') and text[3:].strip() == '':
+                    assert all(x == 32 for x in block[80 * (c + 1):]), 'header block is not blank-padded after END'
+                    done = True
+                    break
+                cards.append(text)
+        def value(key):
+            for text in cards:
+                if text[:8].rstrip() == key and text[8:10] == '= ':
+                    return text[10:].split('/')[0].strip()
+            return None
+        mandatory = [c[:8].rstrip() for c in cards[:3]]
+        assert mandatory[0] == ('SIMPLE' if first else 'XTENSION') and mandatory[1:] == ['BITPIX', 'NAXIS'], mandatory
+        if first:
+            assert value('SIMPLE') == 'T'
+        else:
+            assert value('XTENSION').strip("'").strip() == 'IMAGE' and value('PCOUNT') == '0' and value('GCOUNT') == '1'
+        bitpix, naxis = int(value('BITPIX')), int(value('NAXIS'))
+        assert bitpix in (8, 16, 32, 64, -32, -64)
+        axes = []
+        for k in range(naxis):
+            assert cards[3 + k][:8].rstrip() == 'NAXIS%d' % (k + 1), 'NAXISn cards must follow NAXIS in order'
+            axes.append(int(value('NAXIS%d' % (k + 1))))
+        nbytes = abs(bitpix) // 8 * int(np.prod(axes)) if naxis else 0
+        data = raw[pos:pos + nbytes]
+        assert len(data) == nbytes, 'data unit is truncated'
+        padded = (nbytes + 2879) // 2880 * 2880
+        assert all(b == 0 for b in raw[pos + nbytes:pos + padded]), 'data unit is not zero-padded to a block'
+        pos += padded
+        if naxis:
+            dtype = {-32: '>f4', -64: '>f8', 32: '>i4', 16: '>i2', 8: 'u1', 64: '>i8'}[bitpix]
+            name = (value('EXTNAME') or "'PRIMARY'").strip("'").strip()
+            hdus[name] = np.frombuffer(data, dtype=dtype).reshape(axes[::-1])
+        first = False
+    return hdus
+
+
+class TestWriterAndMosaicDetails:
+    @pytest.mark.gpu
+    def test_written_cube_is_standard_fits(self, tmp_path):
+        """§8 f-4: the combined cube written by Cube.write is valid FITS for a reader that shares no code with the
+        writer, and holds the float32 images of the result (NaN where nothing was combined)."""
+        rng = np.random.default_rng(3)
+        shape = (4, 7, 9)
+        data = [(10 + rng.standard_normal(shape)).astype(np.float32) for _ in range(5)]
+        var = [rng.uniform(0.5, 2, shape).astype(np.float32) for _ in range(5)]
+        for d in data:
+            d[0, 0, :] = np.nan
+        from helpers import write_exposures
+        files = write_exposures(tmp_path, data, var)
+        cube, expmap, _ = CubeList(files).combine(nclip=3.0)
+        out = str(tmp_path / 'combined.fits')
+        cube.write(out)
+        hdus = _fits_standard_check(out)
+        assert set(hdus) >= {'DATA', 'STAT'}
+        assert hdus['DATA'].shape == shape and hdus['DATA'].dtype == np.dtype('>f4')
+        np.testing.assert_array_equal(hdus['DATA'].astype(np.float32), cube.data.astype(np.float32))
+        np.testing.assert_array_equal(hdus['STAT'].astype(np.float32), cube.var.astype(np.float32))
+        assert np.isnan(hdus['DATA'][0, 0]).all()
+        for f in files:                                     # the inputs written by the same writer pass the same check
+            _fits_standard_check(f)
+
+    @pytest.mark.gpu
+    def test_pycombine_streams_planes_and_writes_reference_keywords(self, tmp_path, monkeypatch):
+        """§8 f-3: the py route places the exposures a few planes at a time (bounded host memory), counters and
+        rejmap accumulate over the chunks, and the provenance keywords are the reference's (cubelist.py:199-205)."""
+        import oracle
+        rng = np.random.default_rng(4)
+        shape = (9, 8, 10)
+        n = 6
+        data = [(10 + rng.standard_normal(shape)).astype(np.float32) for _ in range(n)]
+        var = [rng.uniform(0.5, 2, shape).astype(np.float32) for _ in range(n)]
+        for d in data:
+            d[rng.random(shape) < 0.05] = np.nan
+            d[rng.random(shape) < 0.03] += 30
+        from helpers import write_exposures
+        files = write_exposures(tmp_path, data, var)
+        want = oracle.combine_port(data, var, nclip=3.0)
+        whole = CubeList(files).pycombine(nclip=3.0)
+        monkeypatch.setenv('MPDAF_B200_PYCOMBINE_BYTES', str(2 * n * 80 * 4 * 2))      # two planes per chunk
+        parts = CubeList(files).pycombine(nclip=3.0)
+        for cube, expmap, statpix, rejmap in (whole, parts):
+            np.testing.assert_array_equal(expmap.data.ravel(), want['expmap'])
+            np.testing.assert_allclose(cube.data.ravel(), want['data'], rtol=1e-6, equal_nan=True)
+            np.testing.assert_allclose(cube.var.ravel(), want['var'], rtol=1e-6, equal_nan=True)
+            np.testing.assert_array_equal(statpix['NPIX_REJECTED'], want['valid_pix'] - want['select_pix'])
+            nvalid = sum((~np.isnan(d)).astype(np.int32) for d in data)
+            np.testing.assert_array_equal(rejmap.data, nvalid - expmap.data)
+            names = [cube.primary_header['HIERARCH MPDAF METH1 PARAM%d NAME' % k][0] for k in range(1, 6)]
+            assert names == ['nmax', 'nclip_low', 'nclip_up', 'var', 'mad']
+            assert cube.primary_header['HIERARCH MPDAF METH1 ID'][0] == 'obj.cubelist.pycombine'
+
+    @pytest.mark.gpu
+    def test_device_resident_cube_brings_its_finite_mask(self):
+        """§8 f-1: for a device-resident stack the ~isfinite mask of the result is built on the device."""
+        from mpdaf_b200 import synth
+        shape, n = (5, 20, 24), 12
+        stack, _, _ = synth.device_stack(n, shape, seed=3, device=0)
+        cube, expmap, _ = CubeList.from_arrays(stack).combine(nclip=3.0)
+        assert cube._mask is not None and cube._mask.dtype == bool and cube._mask.shape == cube.data.shape
+        np.testing.assert_array_equal(cube.mask, ~np.isfinite(cube.data))
+        assert cube.mask.any() and not cube.mask.all()
+        med, _, _ = CubeList.from_arrays(stack).median()
+        np.testing.assert_array_equal(med.mask, ~np.isfinite(med.data))
