@@ -28,9 +28,14 @@ struct MedianPipeCfg {
     static constexpr int c_regs = 2048 / (2 * NB + 40) - 1;                    // two voxels of NB samples per lane
     static constexpr int C = c_regs < 15 ? (c_regs < 2 ? 2 : c_regs) : 15;       // consumer warps (+ 1 producer warp)
     static constexpr int st_fit = (200 * 1024) / stage_bytes;
-    static constexpr int ST = st_fit > 64 ? 64 : st_fit;                        // ring stages
+    // Ring stages: a multiple of C, so that stage s is only ever consumed by warp s % C and its tiles are taken in
+    // order.  (With an arbitrary ring length the warp waiting for a stage's tile k + 2 ST can overtake the warp that
+    // still owes tile k + ST: an mbarrier wait only knows the PARITY of the phase it waits for, the earlier phase
+    // of equal parity has completed, the wait returns at once, and the kernel reads a stale tile and later hangs.)
+    static constexpr int st_mult = st_fit / C > 4 ? 4 : st_fit / C;
+    static constexpr int ST = st_mult * C;
     static constexpr int threads = (C + 1) * 32;
-    static_assert(ST >= C, "stack too deep for the pipelined median kernel");
+    static_assert(st_mult >= 1, "stack too deep for the pipelined median kernel");
 };
 
 template <int NB>

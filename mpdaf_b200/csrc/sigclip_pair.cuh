@@ -64,10 +64,11 @@ struct PairCfg {
     static constexpr int c_smem = (budget - 2 * stage_bytes) / (stage_bytes + col_bytes);
     static constexpr int c_auto = c_regs < 15 ? (c_regs < c_smem ? c_regs : c_smem) : (15 < c_smem ? 15 : c_smem);
     static constexpr int C = MB_PAIR_CONSUMERS ? MB_PAIR_CONSUMERS : c_auto;
-    // ring stages: a stage is held from the TMA request to the end of its consumer's pass 1; C of them are in
-    // use at the start of a phase-locked round, the rest is lookahead
+        // The ring length is a multiple of C: stage s is then only ever consumed by warp s % C, in order.  (An mbarrier
+    // wait only knows the PARITY of the phase it waits for; with an arbitrary ring length a warp that runs two uses
+    // of a stage ahead of another would see the earlier phase of equal parity completed and read a stale tile.)
     static constexpr int st_fit = (budget - C * col_bytes) / stage_bytes;
-    static constexpr int ST = MB_PAIR_LOOKAHEAD ? C + MB_PAIR_LOOKAHEAD : (st_fit > C + 4 ? C + 4 : st_fit);
+    static constexpr int ST = (st_fit / C > 2 ? 2 : st_fit / C) * C;
     static constexpr int threads = (C + 1) * 32;       // consumers + one producer warp
     static_assert(C >= 2 && ST >= C, "stack too deep for the pair kernel");
 };

@@ -3,7 +3,7 @@
 
 For every depth the slab is sized to ~6 GB of float32 samples (throughput per voxel does not
 depend on nz); prints one JSON line per (N, mode) with kernel time, Gvoxel.exposures/s and the
-achieved fraction of the measured HBM peak.  Usage: python tools/sweep.py > profiles/r01_sweep.jsonl
+achieved fraction of the measured HBM peak.  Usage: python tools/sweep.py > profiles/r02_sweep.jsonl
 """
 import json
 import os
@@ -27,8 +27,9 @@ def main():
     for n in DEPTHS:
         for name, flags in MODES:
             planes_per_voxel = n * (2 if "propagate" in name else 1)
-            budget = 6e9 if n <= 64 and "mad" not in name else 3e8      # the generic kernels are slow: small slabs
-            nz = max(2, min(512, int(budget / (planes_per_voxel * 4 * PLANE))))
+            # ~6 GB of samples per case and never fewer than 32 planes: 3.4 Mvoxel fill the 148 SMs many times over
+            # (round 1 ran the deep rows on 2-7 planes: 0.15 ms kernels, not throughput measurements)
+            nz = max(32, min(512, int(6e9 / (planes_per_voxel * 4 * PLANE))))
             if quick and n not in (12, 48, 96):
                 continue
             cmd = [sys.executable, os.path.join(ROOT, "tools", "run_case.py"), "--n", str(n), "--nz", str(nz),
