@@ -189,6 +189,8 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         ctx.slow_q = j.slow_q ? j.slow_q : g_dev[device].slow_q;     // slab slots bring their own queue (one per stream)
         ctx.slow_n = j.slow_q ? j.slow_n : g_dev[device].slow_n;
         ctx.slow_cap = j.slow_q ? j.slow_cap : kSlowQueueCap;
+        // tests shrink the queue to exercise the overflow route (voxels recomputed in place by the main kernel)
+        if (const char* cap = std::getenv("MPDAF_B200_SLOW_CAP")) ctx.slow_cap = std::min<unsigned>(ctx.slow_cap, (unsigned)std::atoi(cap));
         ctx.stream = stream;
         ctx.name = name;
         ctx.name_len = sizeof name;
@@ -212,6 +214,8 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         ctx.slow_q = j.slow_q ? j.slow_q : g_dev[device].slow_q;     // slab slots bring their own queue (one per stream)
         ctx.slow_n = j.slow_q ? j.slow_n : g_dev[device].slow_n;
         ctx.slow_cap = j.slow_q ? j.slow_cap : kSlowQueueCap;
+        // tests shrink the queue to exercise the overflow route (voxels recomputed in place by the main kernel)
+        if (const char* cap = std::getenv("MPDAF_B200_SLOW_CAP")) ctx.slow_cap = std::min<unsigned>(ctx.slow_cap, (unsigned)std::atoi(cap));
         ctx.stream = stream;
         ctx.name = name;
         ctx.name_len = sizeof name;

@@ -651,3 +651,23 @@ def test_outputs_stay_inside_their_buffers(family):
             assert bool((t[:pad] == -7).all()) and bool((t[pad + nvox:] == -7).all()), (nvox, cuda().kernel_name())
             assert not bool((t[pad:pad + nvox] == -7).any())
         assert (valid == nvox).all()
+
+
+def test_slow_queue_overflow_is_recomputed_in_place(monkeypatch):
+    """Voxels the pair kernel cannot certify go to a queue for the exact kernel; when the queue is full the main kernel
+    recomputes them itself.  Heavy ties (integer data) queue most voxels; a 5-entry queue overflows at once."""
+    rng = np.random.default_rng(77)
+    n = 24
+    data, var = random_stack(rng, n, (6, 13, 17), nan_frac=0.1, outlier_frac=0.05, ties=True)
+    kw = dict(scales=np.linspace(0.9, 1.1, n), offsets=np.linspace(-0.1, 0.1, n), nclip=1.5, nmax=5)
+    want = oracle.combine_port(data, var, **kw)
+    for cap in ("5", "0", None):
+        if cap is None:
+            monkeypatch.delenv("MPDAF_B200_SLOW_CAP", raising=False)
+        else:
+            monkeypatch.setenv("MPDAF_B200_SLOW_CAP", cap)
+        cuda().slow_voxels()
+        got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
+        assert "sigclip_pair<24" in cuda().kernel_name()
+        assert_same_result(got, want)
+        assert cuda().slow_voxels() > 100
