@@ -127,7 +127,7 @@ __device__ __noinline__ void exact_voxel_store(const PairArgs<NB>& S, const Clip
     double mean = CUDART_NAN, sigma = 0.0, ov = CUDART_NAN;
     int kept = n;
     if (n == 1) mean = g.w[0];
-    if (n >= 2) kept = clip_generic<NB>(g, n, A.nmax, A.nclip_low, A.nclip_up, A.nstop < 1 ? 1 : A.nstop, 0, mean, sigma);
+    if (n >= 2) kept = clip_generic<NB>(g, n, A.nmax, A.nclip_low, A.nclip_up, A.nstop < 1 ? 1 : A.nstop, A.mad, mean, sigma);
     if (n >= 1) {
         if (A.typ_var == 0) {
             double vs = 0.0;
@@ -226,6 +226,23 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
             double dev = 0.0;
             for (int j = 0; j < n; j++) dev += (fw[j] - mean) * (fw[j] - mean);
             sigma = sqrt(dev / n);
+            // MAD variant (tools.c:54-77, :122-158): sigma = 1.4826 * median(|w - median|); the deviations of an ascending
+            // run are two sorted runs left and right of the median, merged outward (every lane computes the same value)
+            auto mad_sigma = [&](int lo, int hi) -> double {
+                const int m = hi - lo;
+                const int ihh = lo + (m >> 1);
+                const double med = (m & 1) ? sw[ihh] : (sw[ihh] + sw[ihh - 1]) / 2;
+                int jl = (m & 1) ? ihh : ihh - 1, jr = jl + 1;
+                double cur = 0.0, prev = 0.0;
+                for (int k = 0; k <= (m >> 1); k++) {
+                    const double dl = jl >= lo ? fabs(sw[jl] - med) : CUDART_INF;
+                    const double dr = jr < hi ? fabs(sw[jr] - med) : CUDART_INF;
+                    prev = cur;
+                    if (dl <= dr) { cur = dl; jl--; } else { cur = dr; jr++; }
+                }
+                return ((m & 1) ? cur : (cur + prev) / 2) * 1.4826;
+            };
+            if (A.mad) sigma = mad_sigma(0, n);
             int it = A.nmax;
             for (;;) {
                 const int m = b - a;
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
                 mean = acc / ni;
                 dev = 0.0;
                 for (int j = a; j < b; j++) dev += (sw[j] - mean) * (sw[j] - mean);
-                sigma = sqrt(dev / ni);
+                sigma = A.mad ? mad_sigma(a, b) : sqrt(dev / ni);
             }
         }
         const int kept = b - a;
@@ -320,7 +337,7 @@ __device__ __forceinline__ void sort_pairs(unsigned (&a)[NB])
 // ring stage k % ST and is processed by consumer warp k % C.  flags & 1: the consumer warps start every
 // round of C tiles together (named barrier), so that a line of the long straight-line loop body is fetched
 // once per SM and round instead of once per warp.
-template <int NB, bool UNIT, bool PROP>
+template <int NB, bool UNIT, bool PROP, bool MAD = false>
 __global__ void __launch_bounds__(PairCfg<NB>::threads, 1)
 sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntiles, unsigned* __restrict__ slow_q,
                     unsigned* __restrict__ slow_n, const unsigned slow_cap, const int flags, const __grid_constant__ TmaMaps M)
@@ -525,19 +542,46 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 const double dm1 = T1[h] * rm;
                 const double var_k = __fma_rn(S2[h], rm, -(dm1 * dm1));
                 // conditioning: the moment variance must dominate its rounding error; and it must sit in float32 range
-                if (!(var_k >= 0x1p-13 * (S2_0[h] * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100)) { slow[h] = done[h] = true; continue; }
+                // (MAD: the moments only give the mean; sigma comes from the keys, its uncertainty is part of Tb below)
+                if (!MAD && (!(var_k >= 0x1p-13 * (S2_0[h] * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100))) { slow[h] = done[h] = true; continue; }
                 varl[h] = var_k;
-                if (itl[h] <= 0) { done[h] = true; continue; }                       // tools.c:104: no clip left, these statistics stand
-                float sg;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(__double2float_rn(var_k)));   // 2^-21 relative in all
+                if (itl[h] <= 0) { done[h] = true; continue; }                       // tools.c:104 / :144: no clip left, these statistics stand
                 const int ih = a[h] + (m >> 1);
                 const int il = ih - 1 + (m & 1);
                 const float kh = keyf(ih, h), kl = keyf(il, h);
                 const float km = 0.5f * (kh + kl);                                   // median of the keys (tools.c:45-48)
+                const float emed = krel32 * fmaxf(fabsf(kh), fabsf(kl)) + e0[h];     // its distance from the samples' median
+                float sg, esg = 0.f;
+                if constexpr (MAD) {
+                    // sigma = 1.4826 * median(|w - median|) (tools.c:67-74): the middle of the absolute deviations is found
+                    // by merging the two sorted runs left and right of the median outward, on the keys.  A key deviation
+                    // differs from its sample's by <= e(key) + emed, and only samples within about one MAD of the median
+                    // decide the middle, so the MAD from the keys is within emad of the reference's.
+                    int jl = il, jr = il + 1;
+                    float dl = fabsf(keyf(jl, h) - km), dr = jr < b[h] ? fabsf(keyf(jr, h) - km) : CUDART_INF_F;
+                    float cur = 0.f, prev = 0.f;
+                    for (int s2 = 0; s2 <= (m >> 1); s2++) {
+                        prev = cur;
+                        if (dl <= dr) {
+                            cur = dl;
+                            jl--;
+                            dl = jl >= a[h] ? fabsf(keyf(jl, h) - km) : CUDART_INF_F;
+                        } else {
+                            cur = dr;
+                            jr++;
+                            dr = jr < b[h] ? fabsf(keyf(jr, h) - km) : CUDART_INF_F;
+                        }
+                    }
+                    const float madk = (m & 1) ? cur : 0.5f * (cur + prev);
+                    sg = madk * 1.4826f;
+                    esg = 1.4826f * (krel32 * 1.02f * (fabsf(km) + madk) + e0[h] + emed) + 0x1p-20f * sg;
+                } else {
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(__double2float_rn(var_k)));   // 2^-21 relative in all
+                }
                 const float lo_s = nlo32 * sg, up_s = nup32 * sg;
                 const float clo = km - lo_s, cup = km + up_s;
-                // uncertainty of a bound: key median (KREL |key| + e0), sigma, float32 roundings of this very arithmetic
-                const float Tb = krel32 * fmaxf(fabsf(kh), fabsf(kl)) + e0[h] + 0x1p-19f * (fabsf(km) + lo_s + up_s);
+                // uncertainty of a bound: key median, sigma, float32 roundings of this very arithmetic
+                const float Tb = emed + fmaxf(nlo32, nup32) * esg + 0x1p-19f * (fabsf(km) + lo_s + up_s);
                 if (!(Tb < 0x1p100f)) { slow[h] = done[h] = true; continue; }        // NaN / inf bounds
                 // a key in (kL2, kU2) belongs to a sample that is certainly inside the window
                 const float yl = clo + Tb + e0[h], xu = cup - Tb - e0[h];

@@ -91,7 +91,10 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
     } else {
         const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;   // read per call: tests switch kernel families
         const bool need_var = j.a.typ_var == 0;
-        if (off || j.a.mad || j.median || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL) return MPDAF_B200_OK;
+        if (off || j.median || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL) return MPDAF_B200_OK;
+        // MAD: with var = 'propagate' only (sigma then feeds nothing but decisions; the 'stat' variances would need the
+        // exact MAD of the last set and stay on the warp kernel, which is bit-identical to the reference there)
+        if (j.a.mad && !need_var) return MPDAF_B200_OK;
         // 49 .. 64 exposures with var = 'propagate': nine consumer warps and 128 unsorted-key registers leave the pair
         // kernel behind the warp kernel (2290 vs 2580 GB/s at N = 64, profiles/r02_depth_sweep.txt); it still wins without STAT
         if (NB > 48 && need_var && std::getenv("MPDAF_B200_PAIR_ALWAYS") == nullptr) return MPDAF_B200_OK;
@@ -149,6 +152,11 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             return MPDAF_B200_OK;
         };
         taken = true;
+        if (j.a.mad) {
+            std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s,mad>", NB, unit ? "unit" : "scaled");
+            if (unit) return launch(sigclip_pair_kernel<NB, true, true, true>, sigclip_pair_slow_kernel<NB, true>);
+            return launch(sigclip_pair_kernel<NB, false, true, true>, sigclip_pair_slow_kernel<NB, false>);
+        }
         if (unit) return need_var ? launch(sigclip_pair_kernel<NB, true, true>, sigclip_pair_slow_kernel<NB, true>)
                                   : launch(sigclip_pair_kernel<NB, true, false>, sigclip_pair_slow_kernel<NB, true>);
         return need_var ? launch(sigclip_pair_kernel<NB, false, true>, sigclip_pair_slow_kernel<NB, false>)

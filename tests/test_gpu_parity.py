@@ -309,8 +309,9 @@ def test_ill_conditioned_and_extreme_values():
                        oracle.combine_port(data, var, nclip=2.0, vartype="stat_one"), exact_data=True)
 
 
-def test_mad_is_bit_exact():
-    """The MAD variant runs the reference algorithm on exact sorted values: everything identical."""
+def test_mad_is_bit_exact(monkeypatch):
+    """The MAD variant of the warp kernel runs the reference algorithm on exact sorted values: everything identical."""
+    monkeypatch.setenv("MPDAF_B200_NO_PAIR", "1")
     rng = np.random.default_rng(77)
     c = cuda()
     for n, ties in ((7, False), (16, True), (48, False), (64, True), (100, False)):
@@ -324,6 +325,30 @@ def test_mad_is_bit_exact():
                     assert_same_result(got, want, exact_data=True)
                     if vartype == "stat_one":
                         np.testing.assert_array_equal(got["var"], want["var"])
+
+
+def test_mad_in_the_pair_kernel():
+    """mad=True with var='propagate' on pitched stacks up to 48 deep runs in the pair kernel: sigma = 1.4826 * MAD is
+    taken from the sorted keys with its uncertainty folded into the clip bounds' margin, decisions (expmap, counters)
+    stay identical to the reference, means within a few ulp, propagated variances within the float32-chain bound."""
+    rng = np.random.default_rng(78)
+    c = cuda()
+    for n, ties in ((7, False), (12, True), (24, False), (48, False), (48, True)):
+        data, var = random_stack(rng, n, (5, 13, 17), nan_frac=0.12, outlier_frac=0.06, ties=ties)
+        # (offsets not symmetric about 0: integer data with symmetric offsets has voxels whose mean cancels to rounding
+        # noise, where a relative tolerance means nothing)
+        for kw in (dict(), dict(scales=np.linspace(0.7, 1.4, n), offsets=np.linspace(-1, 1.3, n))):
+            for nclip, nmax in ((2.0, 3), ((1.0, 3.0), 2), (5.0, 2), (3.0, 0)):
+                want = oracle.combine_port(data, var, mad=True, nclip=nclip, vartype="propagate", nmax=nmax, **kw)
+                got = c.combine_cuda(data, var, mad=True, nclip=nclip, vartype="propagate", nmax=nmax,
+                                     location="device_pitched", **kw)
+                assert "sigclip_pair<" in c.kernel_name() and "mad" in c.kernel_name()
+                assert_same_result(got, want)
+                np.testing.assert_allclose(got["data"], want["data"], rtol=1e-12, atol=0, equal_nan=True)
+    # the statistical variances need the exact MAD: they stay on the warp kernel
+    got = c.combine_cuda(data, var, mad=True, nclip=2.0, vartype="stat_one", location="device_pitched")
+    assert "sigclip_warp<" in c.kernel_name()
+    assert_same_result(got, oracle.combine_port(data, var, mad=True, nclip=2.0, vartype="stat_one"), exact_data=True)
 
 
 def test_random_fuzz_against_oracle():
@@ -505,7 +530,7 @@ def test_infinite_samples(n, location, family):
         gotm = cuda().combine_cuda(data, var, vartype=vartype, nclip=3.0, mad=True, location=location, **kw)
         np.testing.assert_array_equal(gotm["valid_pix"], wantm["valid_pix"])
         np.testing.assert_array_equal(gotm["expmap"][finite], wantm["expmap"][finite])
-        np.testing.assert_array_equal(gotm["data"][finite], wantm["data"][finite])
+        np.testing.assert_allclose(gotm["data"][finite], wantm["data"][finite], rtol=1e-12, atol=0, equal_nan=True)
 
 
 @pytest.mark.parametrize("n", [48, 96, 128])
