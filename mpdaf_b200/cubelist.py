@@ -211,6 +211,21 @@ class CubeList:
         self.flux_scales = scalelist
         self.flux_offsets = offsetlist
 
+    #: devices the host-resident and file routes spread their wavelength slabs over: None = every usable B200 of the box
+    #: (the library's default, MPDAF_B200_DEVICES narrows it), an int = that device only, a sequence = exactly those
+    devices = None
+
+    def _device(self):
+        """`device` argument of a HOST-location call (include/mpdaf_b200.h): ALL_DEVICES or one index."""
+        from .ctools import ALL_DEVICES, check, ctools
+        if self.devices is None:
+            return ALL_DEVICES
+        if isinstance(self.devices, (int, np.integer)):
+            return int(self.devices)
+        ids = [int(d) for d in self.devices]
+        check(ctools.mpdaf_b200_set_devices(len(ids), (ctypes.c_int * len(ids))(*ids)), 'mpdaf_b200_set_devices')
+        return ALL_DEVICES
+
     @classmethod
     def from_arrays(cls, data, var=None, scalelist=None, offsetlist=None, names=None,
                     primary_header=None, data_header=None):
@@ -343,7 +358,7 @@ class CubeList:
             arrays, _ = self._host_arrays
             keep, dptr = _ptr_table([a.ctypes.data for a in arrays])
             rc = ctools.mpdaf_b200_median_arrays(
-                self.nfiles, dptr, arrays[0].dtype.itemsize, npixels, HOST, 0,
+                self.nfiles, dptr, arrays[0].dtype.itemsize, npixels, HOST, self._device(),
                 data.ctypes.data, expmap.ctypes.data, valid_pix, None)
             check(rc, 'mpdaf_b200_median_arrays')
         else:
@@ -408,7 +423,7 @@ class CubeList:
             keep_d, dptr = _ptr_table([a.ctypes.data for a in arrays])
             keep_v, vptr = (None, None) if vars_ is None else _ptr_table([a.ctypes.data for a in vars_])
             rc = ctools.mpdaf_b200_sigma_clipping_arrays(
-                self.nfiles, dptr, vptr, arrays[0].dtype.itemsize, npixels, HOST, 0,
+                self.nfiles, dptr, vptr, arrays[0].dtype.itemsize, npixels, HOST, self._device(),
                 data.ctypes.data, vardata.ctypes.data, expmap.ctypes.data,
                 scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix,
                 int(nmax), float(nclip_low), float(nclip_up), int(nstop), int(var_mean), int(mad), None)
@@ -503,7 +518,7 @@ class CubeList:
             keep_v, vptr = (None, None) if v is None else _ptr_table([a.ctypes.data for a in v])
             sl = slice(z0 * plane, z1 * plane)
             rc = ctools.mpdaf_b200_sigma_clipping_arrays(
-                n, dptr, vptr, 4, (z1 - z0) * plane, HOST, 0, data[sl].ctypes.data, vardata[sl].ctypes.data,
+                n, dptr, vptr, 4, (z1 - z0) * plane, HOST, self._device(), data[sl].ctypes.data, vardata[sl].ctypes.data,
                 expmap[sl].ctypes.data, scale.ctypes.data, offset.ctypes.data, select_pix, valid_pix,
                 int(nmax), float(nclip_low), float(nclip_up), int(nstop), int(var_mean), int(mad), None)
             check(rc, 'mpdaf_b200_sigma_clipping_arrays')
