@@ -632,17 +632,42 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                     asm volatile("mov.b32 %0, 0;" : "=r"(RH[h][kk]));
                 }
             }
+            // Cosmic-ray-like outliers are high: most passes have no candidate at the low end of any window of the warp
+            // (or none at the high end) and need only one comparison per exposure.
+            const bool any_low = __any_sync(FULLM, (ncl[0] | ncl[1]) != 0), any_high = __any_sync(FULLM, (nch[0] | nch[1]) != 0);
+            if (any_low && any_high) {
 #pragma unroll
-            for (int i = 0; i < NB; i++) {
-                asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
-                    "setp.le.bf16x2 p0|p1, %4, %5;\n\t"
-                    "setp.ge.bf16x2 p2|p3, %4, %6;\n\t"
-                    "@p0 add.u32 %0, %0, %7;\n\t"
-                    "@p1 add.u32 %1, %1, %7;\n\t"
-                    "@p2 add.u32 %2, %2, %7;\n\t"
-                    "@p3 add.u32 %3, %3, %7;\n\t}"
-                    : "+r"(RL[0][i >> 5]), "+r"(RL[1][i >> 5]), "+r"(RH[0][i >> 5]), "+r"(RH[1][i >> 5])
-                    : "r"(ukey[i]), "r"(thr_lo), "r"(thr_hi), "r"(1u << (i & 31)));
+                for (int i = 0; i < NB; i++) {
+                    asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+                        "setp.le.bf16x2 p0|p1, %4, %5;\n\t"
+                        "setp.ge.bf16x2 p2|p3, %4, %6;\n\t"
+                        "@p0 add.u32 %0, %0, %7;\n\t"
+                        "@p1 add.u32 %1, %1, %7;\n\t"
+                        "@p2 add.u32 %2, %2, %7;\n\t"
+                        "@p3 add.u32 %3, %3, %7;\n\t}"
+                        : "+r"(RL[0][i >> 5]), "+r"(RL[1][i >> 5]), "+r"(RH[0][i >> 5]), "+r"(RH[1][i >> 5])
+                        : "r"(ukey[i]), "r"(thr_lo), "r"(thr_hi), "r"(1u << (i & 31)));
+                }
+            } else if (any_high) {
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    asm("{\n\t.reg .pred p2, p3;\n\t"
+                        "setp.ge.bf16x2 p2|p3, %2, %3;\n\t"
+                        "@p2 add.u32 %0, %0, %4;\n\t"
+                        "@p3 add.u32 %1, %1, %4;\n\t}"
+                        : "+r"(RH[0][i >> 5]), "+r"(RH[1][i >> 5])
+                        : "r"(ukey[i]), "r"(thr_hi), "r"(1u << (i & 31)));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    asm("{\n\t.reg .pred p0, p1;\n\t"
+                        "setp.le.bf16x2 p0|p1, %2, %3;\n\t"
+                        "@p0 add.u32 %0, %0, %4;\n\t"
+                        "@p1 add.u32 %1, %1, %4;\n\t}"
+                        : "+r"(RL[0][i >> 5]), "+r"(RL[1][i >> 5])
+                        : "r"(ukey[i]), "r"(thr_lo), "r"(1u << (i & 31)));
+                }
             }
             // ---- part B: the candidates' exact values decide (their samples are still in the stage) ---------------------
 #pragma unroll
