@@ -225,6 +225,28 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         g_last_launches += ctx.launches;
         return rc;
     }
+    // float64 samples, sigma clip, up to 48 exposures on equally pitched rows: the pair kernel with float64 stages
+    if (j.elem == MPDAF_B200_F64 && !j.median && j.nfiles <= 48) {
+        char name[64] = "";
+        LaunchCtx ctx;
+        ctx.sm_count = g_dev[device].sm_count;
+        ctx.slow = g_dev[device].slow;
+        ctx.slow_q = j.slow_q ? j.slow_q : g_dev[device].slow_q;
+        ctx.slow_n = j.slow_q ? j.slow_n : g_dev[device].slow_n;
+        ctx.slow_cap = j.slow_q ? j.slow_cap : kSlowQueueCap;
+        if (const char* cap = std::getenv("MPDAF_B200_SLOW_CAP")) ctx.slow_cap = std::min<unsigned>(ctx.slow_cap, (unsigned)std::atoi(cap));
+        ctx.stream = stream;
+        ctx.name = name;
+        ctx.name_len = sizeof name;
+        bool taken = false;
+        const int rc = j.nfiles <= 12 ? mb_launch_pair64_12(j, unit, ctx, taken)
+                     : j.nfiles <= 24 ? mb_launch_pair64_24(j, unit, ctx, taken) : mb_launch_pair64_48(j, unit, ctx, taken);
+        if (rc != MPDAF_B200_OK || taken) {
+            g_last_kernel = name;
+            g_last_launches += ctx.launches;
+            return rc;
+        }
+    }
     if (j.nfiles <= 128) {
         if (j.elem == MPDAF_B200_F32) return launch_generic<128, float>(j, device, stream);
         return launch_generic<128, double>(j, device, stream);

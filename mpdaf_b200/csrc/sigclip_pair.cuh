@@ -40,8 +40,8 @@ namespace mb {
 
 template <int NB>
 struct PairArgs {
-    const float* data0;                    // row 0 of the DATA stack
-    const float* var0;                     // row 0 of the STAT stack (null unless var = 'propagate')
+    const void* data0;                     // row 0 of the DATA stack (float32 or float64 samples: template parameter ET)
+    const void* var0;                      // row 0 of the STAT stack (null unless var = 'propagate')
     unsigned long long dstride, vstride;   // elements between consecutive rows
     double2 os[NB];                        // (offset, scale)
     double osp[NB];                        // offset * scale
@@ -52,16 +52,23 @@ struct PairArgs {
     double osmax;                          // max |offset * scale|: part of the absolute key error
 };
 
-template <int NB>
+template <typename ET> struct Vec2;
+template <> struct Vec2<float> { using type = float2; };
+template <> struct Vec2<double> { using type = double2; };
+
+template <int NB, int ES = 4>
 struct PairCfg {
-    static constexpr int stage_bytes = NB * 64 * 4;    // one [NB][64] float32 tile
-    static constexpr int col_bytes = NB * 32 * 4;      // sorted packed keys of one warp
+    static constexpr int stage_bytes = NB * 64 * ES;   // one [NB][64] tile of float32 (ES = 4) or float64 (8) samples
+    static constexpr int col_pad = 5;                  // guard rows below (-inf) and above (+inf) the sorted column: the
+                                                       // clip loop probes up to five ranks beyond either end without clamps
+    static constexpr int col_rows = NB + 2 * col_pad;
+    static constexpr int col_bytes = col_rows * 32 * 4;   // sorted packed keys of one warp
     static constexpr int misc_bytes = 4096;            // barriers, reciprocal table, per-exposure constants
     static constexpr int budget = 227 * 1024 - misc_bytes;
     // consumer warps: bounded by the register file (about 2 NB + 72 registers per thread: sorted and unsorted packed
     // keys plus the per-voxel state), by 15 (four warps per scheduler with the producer), and by shared memory
     static constexpr int c_regs = 2048 / (2 * NB + 72) - 1;
-    static constexpr int c_smem = (budget - 2 * stage_bytes) / (stage_bytes + col_bytes);
+    static constexpr int c_smem = budget / (stage_bytes + col_bytes);     // a stage is held for the whole tile: one per consumer
     static constexpr int c_auto = c_regs < 15 ? (c_regs < c_smem ? c_regs : c_smem) : (15 < c_smem ? 15 : c_smem);
     static constexpr int C = MB_PAIR_CONSUMERS ? MB_PAIR_CONSUMERS : c_auto;
         // The ring length is a multiple of C: stage s is then only ever consumed by warp s % C, in order.  (An mbarrier
@@ -73,15 +80,16 @@ struct PairCfg {
     static_assert(C >= 2 && ST >= C, "stack too deep for the pair kernel");
 };
 
-template <int NB>
+template <int NB, typename ET = float>
 struct PairSmem {
-    float stage[PairCfg<NB>::ST][NB][64];                 // DATA tiles
-    unsigned col[PairCfg<NB>::C][NB][32];                 // sorted keys: low half voxel 2l, high half voxel 2l+1
+    ET stage[PairCfg<NB, sizeof(ET)>::ST][NB][64];        // DATA tiles
+    unsigned col[PairCfg<NB, sizeof(ET)>::C][PairCfg<NB, sizeof(ET)>::col_rows][32];   // guard rows + sorted keys: low half voxel 2l, high half voxel 2l+1
     double rcp[NB + 1];
     double2 os[NB];                                       // (offset, scale) for lane-dependent lookups
     float2 kso[NB];                                       // float32 (scale, offset * scale), likewise
-    unsigned long long full[PairCfg<NB>::ST];             // TMA completion of a stage's DATA tile
-    unsigned long long empty[PairCfg<NB>::ST];            // consumer has finished with the stage
+    double osp[NB];                                       // offset * scale exactly as pass 1 uses it
+    unsigned long long full[PairCfg<NB, sizeof(ET)>::ST];    // TMA completion of a stage's DATA tile
+    unsigned long long empty[PairCfg<NB, sizeof(ET)>::ST];   // consumer has finished with the stage
 };
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
@@ -109,14 +117,16 @@ constexpr unsigned kPairSent = 0xFF7F0000u;   // float32 image of the most negat
 
 // The reference algorithm restated literally for one voxel of a strided stack; stores the outputs and corrects
 // the per-exposure `selected` counters (the main kernel counted every valid sample of a queued voxel as kept).
-template <int NB, bool UNIT>
+template <int NB, bool UNIT, typename ET = float>
 __device__ __noinline__ void exact_voxel_store(const PairArgs<NB>& S, const ClipArgs& A, long long v)
 {
+    const ET* data0 = static_cast<const ET*>(S.data0);
+    const ET* var0 = static_cast<const ET*>(S.var0);
     GenericScratch<NB> g;
     const int nfiles = A.nfiles;
     int n = 0;
     for (int i = 0; i < nfiles; i++) {
-        const float x = __ldg(S.data0 + (size_t)i * S.dstride + v);
+        const ET x = __ldg(data0 + (size_t)i * S.dstride + v);
         if (x == x) {
             g.w[n] = UNIT ? (double)x : (S.os[i].x + (double)x) * S.os[i].y;
             g.file[n] = (unsigned short)i;
@@ -133,7 +143,7 @@ __device__ __noinline__ void exact_voxel_store(const PairArgs<NB>& S, const Clip
             double vs = 0.0;
             for (int k = 0; k < kept; k++) {                                       // merging.c:461-462
                 const int i = g.file[g.idx[k]];
-                vs += (double)__ldg(S.var0 + (size_t)i * S.vstride + v) * S.scale2[i];
+                vs += (double)__ldg(var0 + (size_t)i * S.vstride + v) * S.scale2[i];
             }
             ov = vs / ((double)kept * (double)kept);
         } else if (kept > 1) {
@@ -166,7 +176,7 @@ __device__ __noinline__ void exact_voxel_store(const PairArgs<NB>& S, const Clip
 // and redundantly in every lane, the strict window counts are ballots.  Survivors of a clip are a contiguous range
 // of the ascending copy (verified restatement).  Also corrects the per-exposure `selected` counters:
 // the main kernel counted every valid sample of a queued voxel as kept.
-template <int NB, bool UNIT>
+template <int NB, bool UNIT, typename ET = float>
 __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<NB> S, const ClipArgs A, const unsigned* __restrict__ queue,
                                                                 const unsigned* __restrict__ count, unsigned cap,
                                                                 unsigned long long* slow_total)
@@ -175,6 +185,8 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
     __shared__ double s_s[4][64];            // ascending
     __shared__ unsigned char s_f[4][64];     // exposure of the ascending samples
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const ET* data0 = static_cast<const ET*>(S.data0);
+    const ET* var0 = static_cast<const ET*>(S.var0);
     const unsigned nq = min(*count, cap);
     if (blockIdx.x == 0 && threadIdx.x == 0 && slow_total != nullptr) atomicAdd(slow_total, (unsigned long long)*count);
     const int nfiles = A.nfiles;
@@ -190,7 +202,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
 #pragma unroll
         for (int s = 0; s < 2; s++) {
             const int i = lane + 32 * s;
-            const float x = i < nfiles ? __ldg(S.data0 + (size_t)i * S.dstride + v) : CUDART_NAN_F;
+            const ET x = i < nfiles ? __ldg(data0 + (size_t)i * S.dstride + v) : (ET)CUDART_NAN;
             ok[s] = (x == x);
             const double2 os = S.os[i < NB ? i : 0];
             w[s] = UNIT ? (double)x : (os.x + (double)x) * os.y;                 // merging.c:426
@@ -282,7 +294,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
                     const int j = a + lane + 32 * s;
                     if (j < b) {
                         const int i = n >= 2 ? (int)sf[j] : (b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1);
-                        fw[j - a] = (double)__ldg(S.var0 + (size_t)i * S.vstride + v) * S.scale2[i];
+                        fw[j - a] = (double)__ldg(var0 + (size_t)i * S.vstride + v) * S.scale2[i];
                     }
                 }
                 __syncwarp();
@@ -337,18 +349,20 @@ __device__ __forceinline__ void sort_pairs(unsigned (&a)[NB])
 // ring stage k % ST and is processed by consumer warp k % C.  flags & 1: the consumer warps start every
 // round of C tiles together (named barrier), so that a line of the long straight-line loop body is fetched
 // once per SM and round instead of once per warp.
-template <int NB, bool UNIT, bool PROP, bool MAD = false>
-__global__ void __launch_bounds__(PairCfg<NB>::threads, 1)
+template <int NB, bool UNIT, bool PROP, bool MAD = false, typename ET = float>
+__global__ void __launch_bounds__(PairCfg<NB, sizeof(ET)>::threads, 1)
 sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntiles, unsigned* __restrict__ slow_q,
                     unsigned* __restrict__ slow_n, const unsigned slow_cap, const int flags, const __grid_constant__ TmaMaps M)
 {
-    using Cfg = PairCfg<NB>;
+    using Cfg = PairCfg<NB, sizeof(ET)>;
+    using ET2 = typename Vec2<ET>::type;
+    constexpr bool F64 = sizeof(ET) == 8;
     constexpr int C = Cfg::C, ST = Cfg::ST;
     constexpr int W = ExpSet<NB>::W;
     constexpr unsigned FULLM = 0xffffffffu;
-    constexpr unsigned kTileBytes = NB * 64 * sizeof(float);
+    constexpr unsigned kTileBytes = NB * 64 * sizeof(ET);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    PairSmem<NB>& sm = *reinterpret_cast<PairSmem<NB>*>(smem_raw);
+    PairSmem<NB, ET>& sm = *reinterpret_cast<PairSmem<NB, ET>*>(smem_raw);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
@@ -358,6 +372,12 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
     for (int i = tid; i < NB; i += Cfg::threads) {
         sm.os[i] = S.os[i];
         sm.kso[i] = make_float2(S.kscale[i], S.koffset[i]);
+        sm.osp[i] = S.osp[i];
+    }
+    for (int i = tid; i < C * 2 * Cfg::col_pad * 32; i += Cfg::threads) {
+        const int w = i / (2 * Cfg::col_pad * 32), r = (i / 32) % (2 * Cfg::col_pad), l = i & 31;
+        if (r < Cfg::col_pad) sm.col[w][r][l] = 0xFF80FF80u;                           // (-inf, -inf)
+        else sm.col[w][NB + r][l] = 0x7F807F80u;                                       // (+inf, +inf)
     }
     if (tid == 0) {
         for (int s = 0; s < ST; s++) {
@@ -391,7 +411,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
 #pragma unroll
     for (int k = 0; k < W; k++) { cnt_inval[k] = 0u; cnt_drop[k] = 0u; }
     unsigned tiles_done = 0;
-    const unsigned short* colh = reinterpret_cast<const unsigned short*>(&sm.col[c][0][lane]);   // key q of voxel h: colh[q * 64 + h]
+    const unsigned short* colh = reinterpret_cast<const unsigned short*>(&sm.col[c][Cfg::col_pad][lane]);   // key q of voxel h: colh[q * 64 + h], q in -5 .. NB + 4
     auto col16 = [&](int q, int h) -> unsigned { return (unsigned)colh[q * 64 + h]; };
     auto keyf = [&](int q, int h) -> float { return __uint_as_float(col16(q, h) << 16); };
     const float nlo32 = (float)A.nclip_low, nup32 = (float)A.nclip_up;
@@ -414,7 +434,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         const unsigned k = (unsigned)kk64;
         const long long tile = (long long)blockIdx.x + kk64 * gridDim.x;
         const unsigned st = k % ST, ph = (k / ST) & 1u;
-        float (*dt)[64] = sm.stage[st];
+        ET (*dt)[64] = sm.stage[st];
         const long long v0 = (tile << 6) + 2 * lane;            // this lane's voxels: v0, v0 + 1
         // the STAT rows of these voxels are read at the end of the tile: start them on their way into L2 now
         if (PROP && lane == 0) tma_prefetch_2d(&M.stat, (int)(tile << 6), 0);
@@ -424,18 +444,27 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         // ---- pivot: median of the first three samples (robust against one outlier), else the fourth, else 0
         float pf[2];
         {
-            const float2 r0 = *reinterpret_cast<const float2*>(&dt[0][2 * lane]);
-            const float2 r1 = *reinterpret_cast<const float2*>(&dt[1][2 * lane]);
-            const float2 r2 = *reinterpret_cast<const float2*>(&dt[2][2 * lane]);
-            const float2 r3 = *reinterpret_cast<const float2*>(&dt[3][2 * lane]);
+            const ET2 r0 = *reinterpret_cast<const ET2*>(&dt[0][2 * lane]);
+            const ET2 r1 = *reinterpret_cast<const ET2*>(&dt[1][2 * lane]);
+            const ET2 r2 = *reinterpret_cast<const ET2*>(&dt[2][2 * lane]);
+            const ET2 r3 = *reinterpret_cast<const ET2*>(&dt[3][2 * lane]);
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                float x0 = h ? r0.y : r0.x, x1 = h ? r1.y : r1.x, x2 = h ? r2.y : r2.x, x3 = h ? r3.y : r3.x;
-                if constexpr (!UNIT) {
-                    x0 = __fmaf_rn(x0, S.kscale[0], S.koffset[0]);
-                    x1 = __fmaf_rn(x1, S.kscale[1], S.koffset[1]);
-                    x2 = __fmaf_rn(x2, S.kscale[2], S.koffset[2]);
-                    x3 = __fmaf_rn(x3, S.kscale[3], S.koffset[3]);
+                float x0, x1, x2, x3;
+                if constexpr (F64) {
+                    const double y0 = h ? r0.y : r0.x, y1 = h ? r1.y : r1.x, y2 = h ? r2.y : r2.x, y3 = h ? r3.y : r3.x;
+                    x0 = __double2float_rn(UNIT ? y0 : __fma_rn(y0, S.os[0].y, S.osp[0]));
+                    x1 = __double2float_rn(UNIT ? y1 : __fma_rn(y1, S.os[1].y, S.osp[1]));
+                    x2 = __double2float_rn(UNIT ? y2 : __fma_rn(y2, S.os[2].y, S.osp[2]));
+                    x3 = __double2float_rn(UNIT ? y3 : __fma_rn(y3, S.os[3].y, S.osp[3]));
+                } else {
+                    x0 = h ? r0.y : r0.x, x1 = h ? r1.y : r1.x, x2 = h ? r2.y : r2.x, x3 = h ? r3.y : r3.x;
+                    if constexpr (!UNIT) {
+                        x0 = __fmaf_rn(x0, S.kscale[0], S.koffset[0]);
+                        x1 = __fmaf_rn(x1, S.kscale[1], S.koffset[1]);
+                        x2 = __fmaf_rn(x2, S.kscale[2], S.koffset[2]);
+                        x3 = __fmaf_rn(x3, S.kscale[3], S.koffset[3]);
+                    }
                 }
                 float m3 = fmaxf(fminf(x0, x1), fminf(fmaxf(x0, x1), x2));   // fminf / fmaxf skip NaNs
                 m3 = (m3 == m3) ? m3 : x3;
@@ -457,19 +486,17 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         double T1[2] = {0.0, 0.0}, S2[2] = {0.0, 0.0};
 #pragma unroll
         for (int i = 0; i < NB; i++) {
-            const float2 dd = *reinterpret_cast<const float2*>(&dt[i][2 * lane]);
+            const ET2 dd = *reinterpret_cast<const ET2*>(&dt[i][2 * lane]);
             double t[2];
             float tf[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                const float d = h ? dd.y : dd.x;
-                if constexpr (UNIT) {
-                    t[h] = (double)d - p[h];
-                    tf[h] = d - pf[h];
-                } else {
-                    t[h] = __fma_rn((double)d, S.os[i].y, S.osp[i] - p[h]);      // (offset + d) * scale - pivot, merging.c:426
-                    tf[h] = __fmaf_rn(d, S.kscale[i], S.koffset[i]) - pf[h];
-                }
+                const ET d = h ? dd.y : dd.x;
+                if constexpr (UNIT) t[h] = (double)d - p[h];
+                else t[h] = __fma_rn((double)d, S.os[i].y, S.osp[i] - p[h]);     // (offset + d) * scale - pivot, merging.c:426
+                if constexpr (F64) tf[h] = __double2float_rn(t[h]);               // float64 samples: the key value is float32(t)
+                else if constexpr (UNIT) tf[h] = (float)d - pf[h];
+                else tf[h] = __fmaf_rn((float)d, S.kscale[i], S.koffset[i]) - pf[h];
             }
             {
                 asm("{\n\t.reg .pred q0, q1;\n\t.reg .b32 lo0, hi0, lo1, hi1;\n\t"
@@ -504,7 +531,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         // ---- order the packed keys; sorted column to shared memory ------------------------------------------
         sort_pairs<NB>(key);
 #pragma unroll
-        for (int q = 0; q < NB; q++) sm.col[c][q][lane] = key[q];
+        for (int q = 0; q < NB; q++) sm.col[c][Cfg::col_pad + q][lane] = key[q];
         __syncwarp();
 
         // ---- clip iterations (tools.c:82-118), both voxels in lockstep ---------------------------------------
@@ -528,27 +555,46 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             if (n[h] >= 2 && !(S2[h] < 0x1p200)) { slow[h] = true; done[h] = true; }   // non-finite or absurd values
             e0[h] = 0x1p-21f * (fabsf(pf[h]) + (float)S.osmax) + 0x1p-100f;
         }
+        // The statistics of the set that no clip follows (tools.c:104 / :144).  Only the 'stat' variances need them; with
+        // var = 'propagate' sigma feeds nothing any more and the voxel is simply finished.
+        auto final_stats = [&](int h) {
+            if constexpr (!PROP) {
+                const int m = b[h] - a[h];
+                const double rm = sm.rcp[m];
+                const double dm1 = T1[h] * rm;
+                const double var_k = __fma_rn(S2[h], rm, -(dm1 * dm1));
+                if (!(var_k >= 0x1p-13 * (S2_0[h] * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100)) slow[h] = true;
+                else varl[h] = var_k;
+            }
+            done[h] = true;
+        };
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if (!done[h] && itl[h] <= 0) final_stats(h);
         for (;;) {
             if (!__any_sync(FULLM, !(done[0] && done[1]))) break;
-            unsigned thr_lo = 0xFF80FF80u, thr_hi = 0x7F807F80u;   // (-inf, -inf), (+inf, +inf): match nothing
-            int ncl[2] = {0, 0}, nch[2] = {0, 0};                  // candidates for rejection at the low / high end
-            float clo32[2] = {0.f, 0.f}, cup32[2] = {0.f, 0.f}, tb32[2] = {0.f, 0.f};
+            unsigned thr_lo, thr_hi;                               // packed boundary keys of the two voxels
+            int ncl[2], nch[2];                                    // candidates for rejection at the low / high end
+            float clo32[2], cup32[2], tb32[2];
+            unsigned BLh[2], BUh[2];
             // ---- part A: sigma, bounds, and the keys that are not CERTAINLY inside the window -------------------
+            // Branch-free and evaluated for both voxels of the lane whether or not they are still active (the warp issues
+            // these instructions as long as ANY lane needs them; without branches the two voxels' chains interleave).
+            // Ranks beyond either end of the window read rejected / invalid keys or the guard rows: never fewer candidates.
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                if (done[h]) continue;
+                const bool act = !done[h];
                 const int m = b[h] - a[h];
                 const double rm = sm.rcp[m];
                 const double dm1 = T1[h] * rm;
                 const double var_k = __fma_rn(S2[h], rm, -(dm1 * dm1));
                 // conditioning: the moment variance must dominate its rounding error; and it must sit in float32 range
                 // (MAD: the moments only give the mean; sigma comes from the keys, its uncertainty is part of Tb below)
-                if (!MAD && (!(var_k >= 0x1p-13 * (S2_0[h] * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100))) { slow[h] = done[h] = true; continue; }
-                varl[h] = var_k;
-                if (itl[h] <= 0) { done[h] = true; continue; }                       // tools.c:104 / :144: no clip left, these statistics stand
-                const int ih = a[h] + (m >> 1);
-                const int il = ih - 1 + (m & 1);
-                const float kh = keyf(ih, h), kl = keyf(il, h);
+                const bool bad = !MAD && (!(var_k >= 0x1p-13 * (S2_0[h] * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100));
+                if constexpr (!PROP) varl[h] = (act && !bad) ? var_k : varl[h];
+                const unsigned short* pm = colh + ((a[h] + (m >> 1)) * 64 + h);       // upper middle of the window
+                const float kh = __uint_as_float((unsigned)pm[0] << 16);
+                const float kl = __uint_as_float((unsigned)((m & 1) ? pm[0] : pm[-64]) << 16);
                 const float km = 0.5f * (kh + kl);                                   // median of the keys (tools.c:45-48)
                 const float emed = krel32 * fmaxf(fabsf(kh), fabsf(kl)) + e0[h];     // its distance from the samples' median
                 float sg, esg = 0.f;
@@ -557,24 +603,28 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                     // by merging the two sorted runs left and right of the median outward, on the keys.  A key deviation
                     // differs from its sample's by <= e(key) + emed, and only samples within about one MAD of the median
                     // decide the middle, so the MAD from the keys is within emad of the reference's.
-                    int jl = il, jr = il + 1;
-                    float dl = fabsf(keyf(jl, h) - km), dr = jr < b[h] ? fabsf(keyf(jr, h) - km) : CUDART_INF_F;
-                    float cur = 0.f, prev = 0.f;
-                    for (int s2 = 0; s2 <= (m >> 1); s2++) {
-                        prev = cur;
-                        if (dl <= dr) {
-                            cur = dl;
-                            jl--;
-                            dl = jl >= a[h] ? fabsf(keyf(jl, h) - km) : CUDART_INF_F;
-                        } else {
-                            cur = dr;
-                            jr++;
-                            dr = jr < b[h] ? fabsf(keyf(jr, h) - km) : CUDART_INF_F;
+                    sg = 0.f;
+                    if (act) {
+                        const int il = a[h] + (m >> 1) - 1 + (m & 1);
+                        int jl = il, jr = il + 1;
+                        float dl = fabsf(keyf(jl, h) - km), dr = jr < b[h] ? fabsf(keyf(jr, h) - km) : CUDART_INF_F;
+                        float cur = 0.f, prev = 0.f;
+                        for (int s2 = 0; s2 <= (m >> 1); s2++) {
+                            prev = cur;
+                            if (dl <= dr) {
+                                cur = dl;
+                                jl--;
+                                dl = jl >= a[h] ? fabsf(keyf(jl, h) - km) : CUDART_INF_F;
+                            } else {
+                                cur = dr;
+                                jr++;
+                                dr = jr < b[h] ? fabsf(keyf(jr, h) - km) : CUDART_INF_F;
+                            }
                         }
+                        const float madk = (m & 1) ? cur : 0.5f * (cur + prev);
+                        sg = madk * 1.4826f;
+                        esg = 1.4826f * (krel32 * 1.02f * (fabsf(km) + madk) + e0[h] + emed) + 0x1p-20f * sg;
                     }
-                    const float madk = (m & 1) ? cur : 0.5f * (cur + prev);
-                    sg = madk * 1.4826f;
-                    esg = 1.4826f * (krel32 * 1.02f * (fabsf(km) + madk) + e0[h] + emed) + 0x1p-20f * sg;
                 } else {
                     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(__double2float_rn(var_k)));   // 2^-21 relative in all
                 }
@@ -582,43 +632,40 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 const float clo = km - lo_s, cup = km + up_s;
                 // uncertainty of a bound: key median, sigma, float32 roundings of this very arithmetic
                 const float Tb = emed + fmaxf(nlo32, nup32) * esg + 0x1p-19f * (fabsf(km) + lo_s + up_s);
-                if (!(Tb < 0x1p100f)) { slow[h] = done[h] = true; continue; }        // NaN / inf bounds
+                const bool bad_tb = !(Tb < 0x1p100f);                                 // NaN / inf bounds
                 // a key in (kL2, kU2) belongs to a sample that is certainly inside the window
                 const float yl = clo + Tb + e0[h], xu = cup - Tb - e0[h];
                 const float kL2 = yl * (yl >= 0.f ? c2f : c1f);
                 const float kU2 = xu * (xu >= 0.f ? c1f : c2f);
-                float kl4[5], ku4[5];
-#pragma unroll
-                for (int j = 0; j < 5; j++) {
-                    const int ql = a[h] + j, qu = b[h] - 1 - j;
-                    kl4[j] = ql < b[h] ? keyf(ql < NB ? ql : NB - 1, h) : CUDART_INF_F;
-                    ku4[j] = qu >= a[h] ? keyf(qu >= 0 ? qu : 0, h) : -CUDART_INF_F;
-                }
+                const unsigned short* plo = colh + (a[h] * 64 + h);                    // lowest rank of the window
+                const unsigned short* phi = colh + ((b[h] - 1) * 64 + h);              // highest
                 int jl = 0, ju = 0;
+                bool ql = true, qu = true;
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
-                    jl += (jl == j && !(kl4[j] > kL2)) ? 1 : 0;
-                    ju += (ju == j && !(ku4[j] < kU2)) ? 1 : 0;
+                    ql = ql && !(__uint_as_float((unsigned)plo[64 * j] << 16) > kL2);
+                    qu = qu && !(__uint_as_float((unsigned)phi[-64 * j] << 16) < kU2);
+                    jl += ql ? 1 : 0;
+                    ju += qu ? 1 : 0;
                 }
                 // at most four candidates per side (the probes' reach), and the two ends must not meet
-                if (jl > 4 || ju > 4 || jl + ju > m) { slow[h] = done[h] = true; continue; }
-                if (jl + ju == 0) { done[h] = true; continue; }                     // everything inside: tools.c:100
-                ncl[h] = jl;
-                nch[h] = ju;
+                const bool many = jl > 4 || ju > 4 || jl + ju > m;
+                const bool go_slow = bad || bad_tb || many;
+                const bool cand = act && !go_slow && (jl + ju) != 0;                  // jl + ju == 0: everything inside, tools.c:100
+                slow[h] = slow[h] || (act && go_slow);
+                done[h] = !cand;
+                ncl[h] = cand ? jl : 0;
+                nch[h] = cand ? ju : 0;
                 clo32[h] = clo;
                 cup32[h] = cup;
                 tb32[h] = Tb;
                 // boundary keys: the candidates are the window's keys at or below BL / at or above BU
-                const unsigned BL = jl > 0 ? col16(a[h] + jl - 1, h) : 0xFF80u;
-                const unsigned BU = ju > 0 ? col16(b[h] - ju, h) : 0x7F80u;
-                if (h == 0) {
-                    thr_lo = (thr_lo & 0xFFFF0000u) | BL;
-                    thr_hi = (thr_hi & 0xFFFF0000u) | BU;
-                } else {
-                    thr_lo = (thr_lo & 0x0000FFFFu) | (BL << 16);
-                    thr_hi = (thr_hi & 0x0000FFFFu) | (BU << 16);
-                }
+                const unsigned bl = (unsigned)plo[64 * (jl - 1)], bu = (unsigned)phi[-64 * (ju - 1)];
+                BLh[h] = (cand && jl > 0) ? bl : 0xFF80u;                             // -inf / +inf: match nothing
+                BUh[h] = (cand && ju > 0) ? bu : 0x7F80u;
             }
+            thr_lo = BLh[0] | (BLh[1] << 16);
+            thr_hi = BUh[0] | (BUh[1] << 16);
             if (!__any_sync(FULLM, (ncl[0] | nch[0] | ncl[1] | nch[1]) != 0)) continue;
             // ---- which exposures are those?  one packed comparison pass over the unsorted keys -------------------
             // (invalid samples are NaN in the unsorted keys and match nothing; the bits of a mask word are distinct, so
@@ -702,11 +749,11 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                         const int i = 32 * kk + (__ffs(mw) - 1);
                         mw &= mw - 1u;
                         const bool low = (RL[h][kk] >> (i & 31)) & 1u;
-                        const float dval = dt[i][2 * lane + h];
+                        const ET dval = dt[i][2 * lane + h];
                         const double2 osj = sm.os[i];
                         const float2 ksj = sm.kso[i];
-                        const double t = UNIT ? (double)dval - p[h] : __fma_rn((double)dval, osj.y, osj.x * osj.y - p[h]);
-                        const float t32 = UNIT ? dval - pf[h] : __fmaf_rn(dval, ksj.x, ksj.y) - pf[h];
+                        const double t = UNIT ? (double)dval - p[h] : __fma_rn((double)dval, osj.y, sm.osp[i] - p[h]);
+                        const float t32 = F64 ? __double2float_rn(t) : (UNIT ? (float)dval - pf[h] : __fmaf_rn((float)dval, ksj.x, ksj.y) - pf[h]);
                         unsigned kb;
                         asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(kb) : "f"(t32));
                         const float tk = __uint_as_float(kb & 0xFFFF0000u);          // this sample's key, as in pass 1
@@ -737,6 +784,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 }
                 a[h] += rl;
                 b[h] -= rh;
+                if (itl[h] <= 0) final_stats(h);                                     // no clip left: these statistics stand
             }
         }
         // ---- the samples are consumed: hand the stage back to the producer --------------------------------------
@@ -771,8 +819,33 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
 #pragma unroll
             for (int j = 0; j < NACC; j++) { vacc[0][j] = 0.f; vacc[1][j] = 0.f; }
             unsigned neg = 0u;
-            if (pair_ok) {
-                const float* vp = S.var0 + v0;
+            if constexpr (F64) {
+                // float64 STAT: float64 products (the reference's arithmetic, merging.c:431), loads in batches of 8 rows
+                if (pair_ok) {
+                    const double* vp = static_cast<const double*>(S.var0) + v0;
+                    constexpr int VB = 8;
+#pragma unroll
+                    for (int i0 = 0; i0 < NB; i0 += VB) {
+                        double2 sv[VB];
+#pragma unroll
+                        for (int j = 0; j < VB; j++) {
+                            if (i0 + j < NB) {
+                                asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(sv[j].x), "=d"(sv[j].y) : "l"(vp));
+                                vp += S.vstride;
+                            }
+                        }
+                        asm volatile("" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < VB; j++) {
+                            if (i0 + j < NB) {
+                                if (!drop[0].test(i0 + j)) vsum[0] += sv[j].x * S.scale2[i0 + j];
+                                if (!drop[1].test(i0 + j)) vsum[1] += sv[j].y * S.scale2[i0 + j];
+                            }
+                        }
+                    }
+                }
+            } else if (pair_ok) {
+                const float* vp = static_cast<const float*>(S.var0) + v0;
                 float2 sv[NB];
 #pragma unroll
                 for (int i = 0; i < HB; i++) {
@@ -797,12 +870,13 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             }
             if (!pair_ok || (neg & 0x80000000u)) {
                 // ragged last pair, or a sign bit was seen: float64 products in exposure order (merging.c:431)
+                const ET* var0 = static_cast<const ET*>(S.var0);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     vsum[h] = 0.0;
                     if (v0 + h >= A.nvox) continue;
                     for (int i = 0; i < A.nfiles; i++)
-                        if (!drop[h].test_dyn(i)) vsum[h] += (double)__ldg(S.var0 + (size_t)i * S.vstride + (v0 + h)) * (sm.os[i].y * sm.os[i].y);
+                        if (!drop[h].test_dyn(i)) vsum[h] += (double)__ldg(var0 + (size_t)i * S.vstride + (v0 + h)) * (sm.os[i].y * sm.os[i].y);
                 }
             }
         }
@@ -845,7 +919,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 } else {
                     const unsigned pos = atomicAdd(slow_n, 1u);
                     if (pos < slow_cap) slow_q[pos] = (unsigned)v;
-                    else exact_voxel_store<NB, UNIT>(S, A, v);       // queue full: recompute in place
+                    else exact_voxel_store<NB, UNIT, ET>(S, A, v);   // queue full: recompute in place
                 }
             }
         }

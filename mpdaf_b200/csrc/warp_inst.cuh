@@ -53,7 +53,7 @@ void fill_tile_args(TileArgs<NB>& s, const Job& j)
 // 2-D tensor map over a stack of equally pitched float32 rows: dim 0 = voxels, dim 1 = rows, box 32 x nrows,
 // NaN beyond the last voxel (so the lanes of a ragged last tile see invalid samples).
 inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long long nvox, int nrows, unsigned long long pitch_bytes,
-                             unsigned box_voxels = 32u, int box_rows = 0, bool nan_fill = true)
+                             unsigned box_voxels = 32u, int box_rows = 0, bool nan_fill = true, bool f64 = false)
 {
     using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -72,7 +72,7 @@ inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long l
     const cuuint64_t strides[1] = {pitch_bytes};
     const cuuint32_t box[2] = {box_voxels, (cuuint32_t)(box_rows > 0 ? box_rows : nrows)};
     const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult rc = encode(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+    const CUresult rc = encode(&map, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                nan_fill ? CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA : CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) return false;
@@ -80,13 +80,15 @@ inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long l
     return true;
 }
 
-// Pair-packed TMA-pipelined sigma clip (sigclip_pair.cuh): float32 stacks up to 64 deep whose rows are equally
-// pitched and 16-byte aligned.  Returns MPDAF_B200_OK and sets `taken` when the stack qualifies.
-template <int NB>
+// Pair-packed TMA-pipelined sigma clip (sigclip_pair.cuh): float32 stacks up to 64 deep (float64: up to 48) whose rows
+// are equally pitched and 16-byte aligned.  Returns MPDAF_B200_OK and sets `taken` when the stack qualifies.
+template <int NB, typename ET = float>
 int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
 {
     taken = false;
-    if constexpr (NB > 64) {
+    constexpr long long ES = (long long)sizeof(ET);
+    constexpr bool F64 = sizeof(ET) == 8;
+    if constexpr (NB > 64 || (F64 && NB > 48)) {
         return MPDAF_B200_OK;
     } else {
         const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;   // read per call: tests switch kernel families
@@ -102,10 +104,10 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
             if (j.nfiles == 1) return (unsigned long long)((j.a.nvox + 3) / 4 * 4);
             const long long step = static_cast<const char*>(rows[1]) - static_cast<const char*>(rows[0]);
-            if (step < j.a.nvox * 4 || (step & 15) != 0) return 0ull;
+            if (step < j.a.nvox * ES || (step & 15) != 0) return 0ull;
             for (int i = 2; i < j.nfiles; i++)
                 if (static_cast<const char*>(rows[i]) - static_cast<const char*>(rows[i - 1]) != step) return 0ull;
-            return (unsigned long long)(step >> 2);
+            return (unsigned long long)(step / ES);
         };
         const unsigned long long dp = pitch_of(j.data), vp = need_var ? pitch_of(j.var) : 0ull;
         if (dp == 0 || (need_var && vp == 0)) return MPDAF_B200_OK;
@@ -113,12 +115,12 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             return MPDAF_B200_OK;
         TmaMaps maps;
         std::memset(&maps, 0, sizeof(maps));
-        if (!encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * dp, 64u, NB, true)) return MPDAF_B200_OK;
-        if (need_var && !encode_stack_map(maps.stat, j.var[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * vp, 64u, NB, false)) return MPDAF_B200_OK;
+        if (!encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, (unsigned long long)ES * dp, 64u, NB, true, F64)) return MPDAF_B200_OK;
+        if (need_var && !encode_stack_map(maps.stat, j.var[0], (unsigned long long)j.a.nvox, j.nfiles, (unsigned long long)ES * vp, 64u, NB, false, F64)) return MPDAF_B200_OK;
         PairArgs<NB> s;
         std::memset(&s, 0, sizeof(s));
-        s.data0 = static_cast<const float*>(j.data[0]);
-        s.var0 = need_var ? static_cast<const float*>(j.var[0]) : nullptr;
+        s.data0 = j.data[0];
+        s.var0 = need_var ? j.var[0] : nullptr;
         s.dstride = dp;
         s.vstride = vp;
         double osmax = 0.0;
@@ -134,11 +136,11 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             osmax = std::max(osmax, std::fabs(of * sc));
         }
         s.osmax = osmax;
-        using Cfg = PairCfg<NB>;
-        std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s>", NB, unit ? "unit" : "scaled");
+        using Cfg = PairCfg<NB, sizeof(ET)>;
+        std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s%s>", NB, unit ? "unit" : "scaled", F64 ? ",f64" : "");
         const long long ntiles = (j.a.nvox + 63) / 64;
         auto launch = [&](auto kernel, auto slow_kernel) -> int {
-            const int smem = (int)sizeof(PairSmem<NB>);
+            const int smem = (int)sizeof(PairSmem<NB, ET>);
             MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             MB_CUDA(cudaMemsetAsync(ctx.slow_n, 0, sizeof(unsigned), ctx.stream));
             const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
@@ -153,14 +155,14 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
         };
         taken = true;
         if (j.a.mad) {
-            std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s,mad>", NB, unit ? "unit" : "scaled");
-            if (unit) return launch(sigclip_pair_kernel<NB, true, true, true>, sigclip_pair_slow_kernel<NB, true>);
-            return launch(sigclip_pair_kernel<NB, false, true, true>, sigclip_pair_slow_kernel<NB, false>);
+            std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s,mad%s>", NB, unit ? "unit" : "scaled", F64 ? ",f64" : "");
+            if (unit) return launch(sigclip_pair_kernel<NB, true, true, true, ET>, sigclip_pair_slow_kernel<NB, true, ET>);
+            return launch(sigclip_pair_kernel<NB, false, true, true, ET>, sigclip_pair_slow_kernel<NB, false, ET>);
         }
-        if (unit) return need_var ? launch(sigclip_pair_kernel<NB, true, true>, sigclip_pair_slow_kernel<NB, true>)
-                                  : launch(sigclip_pair_kernel<NB, true, false>, sigclip_pair_slow_kernel<NB, true>);
-        return need_var ? launch(sigclip_pair_kernel<NB, false, true>, sigclip_pair_slow_kernel<NB, false>)
-                        : launch(sigclip_pair_kernel<NB, false, false>, sigclip_pair_slow_kernel<NB, false>);
+        if (unit) return need_var ? launch(sigclip_pair_kernel<NB, true, true, false, ET>, sigclip_pair_slow_kernel<NB, true, ET>)
+                                  : launch(sigclip_pair_kernel<NB, true, false, false, ET>, sigclip_pair_slow_kernel<NB, true, ET>);
+        return need_var ? launch(sigclip_pair_kernel<NB, false, true, false, ET>, sigclip_pair_slow_kernel<NB, false, ET>)
+                        : launch(sigclip_pair_kernel<NB, false, false, false, ET>, sigclip_pair_slow_kernel<NB, false, ET>);
     }
 }
 
@@ -270,6 +272,10 @@ int launch_median_warp_impl(const Job& j, LaunchCtx& ctx)
 }
 
 }  // namespace mb
+
+// float64 samples (BITPIX -64): the pair kernel with float64 stages; `taken` false = the layout does not qualify
+#define MB_DEFINE_PAIR64(NB)                                                                                  \
+    int mb_launch_pair64_##NB(const mb::Job& j, bool unit, mb::LaunchCtx& ctx, bool& taken) { return mb::launch_pair_impl<NB, double>(j, unit, ctx, taken); }
 
 #define MB_DEFINE_DEPTH(NB)                                                                                   \
     int mb_launch_warp_##NB(const mb::Job& j, bool unit, mb::LaunchCtx& ctx) { return mb::launch_warp_impl<NB>(j, unit, ctx); } \

@@ -171,6 +171,41 @@ def test_float64_exposures(location):
     assert_same_result(cuda().median_cuda(data, location=location), oracle.median_port(data), median=True)
 
 
+@pytest.mark.parametrize("n", [2, 5, 12, 13, 24, 37, 48])
+def test_float64_exposures_on_the_pair_kernel(n):
+    """BITPIX -64 stacks up to 48 deep on equally pitched rows: the pair kernel with float64 stages (float64 samples in
+    the moments and in every exact decision, float64 STAT products); every mode, host route included."""
+    rng = np.random.default_rng(300 + n)
+    data, var = random_stack(rng, n, (5, 9, 11), nan_frac=0.1, outlier_frac=0.04, dtype=np.float64)
+    # samples float32 cannot tell apart: the decisions must come from the float64 values
+    data[0] += 1e-9 * rng.standard_normal(data[0].shape)
+    scales = np.linspace(0.9, 1.1, n)
+    offsets = np.linspace(-0.1, 0.1, n)
+    for kw in (dict(), dict(scales=scales, offsets=offsets)):
+        for vartype, nclip, mad in (("propagate", 3.0, False), ("stat_mean", (2.0, 3.0), False), ("stat_one", 5.0, False),
+                                    ("propagate", 2.5, True)):
+            want = oracle.combine_port(data, var, vartype=vartype, nclip=nclip, mad=mad, **kw)
+            got = cuda().combine_cuda(data, var, vartype=vartype, nclip=nclip, mad=mad, location="device_pitched", **kw)
+            assert "sigclip_pair<" in cuda().kernel_name() and "f64" in cuda().kernel_name()
+            assert_same_result(got, want)
+    want = oracle.combine_port(data, var, nclip=3.0)
+    assert_same_result(cuda().combine_cuda(data, var, nclip=3.0, location="host"), want)
+    assert_same_result(cuda().combine_cuda(data, var, nclip=3.0, location="device"), want)     # separate allocations: generic kernel
+
+
+def test_float64_ties_and_non_finite_samples():
+    rng = np.random.default_rng(41)
+    data, var = random_stack(rng, 24, (4, 7, 9), ties=True, dtype=np.float64)
+    data[3][0, 0, :4] = np.inf
+    data[5][0, 1, :4] = -np.inf
+    data[7][0, 2, :4] = 1e300
+    for vartype in ("propagate", "stat_mean"):
+        want = oracle.combine_port(data, var, vartype=vartype, nclip=2.0)
+        got = cuda().combine_cuda(data, var, vartype=vartype, nclip=2.0, location="device_pitched")
+        assert "f64" in cuda().kernel_name()
+        assert_same_result(got, want)
+
+
 def test_edge_cases():
     c = cuda()
     # empty stack

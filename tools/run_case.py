@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--nclip", type=float, default=5.0)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--f64", action="store_true", help="float64 samples (BITPIX -64)")
     ap.add_argument("--check", action="store_true", help="compare the first planes with the oracle port")
     args = ap.parse_args()
 
@@ -45,19 +46,32 @@ def main():
     expmap = torch.empty(nvox, dtype=torch.int32, device=dev)
     scales = synth.default_scales(n) if args.scaled else np.ones(n)
     offsets = synth.default_offsets(n) if args.scaled else np.zeros(n)
-    kd, dptr = _ptr_table(stack.data_ptrs)
-    kv, vptr = (None, None) if stack.var_ptrs is None else _ptr_table(stack.var_ptrs)
+    esz = 4
+    dptrs, vptrs = stack.data_ptrs, stack.var_ptrs
+    if args.f64:    # the same samples as float64, one [n][pitch] allocation per HDU
+        esz = 8
+        pitch = (nvox + 31) // 32 * 32
+        d64 = torch.empty((n, pitch), dtype=torch.float64, device=dev)
+        d64[:, :nvox] = tdata
+        dptrs = [d64[i].data_ptr() for i in range(n)]
+        if tvar is not None:
+            v64 = torch.empty((n, pitch), dtype=torch.float64, device=dev)
+            v64[:, :nvox] = tvar
+            vptrs = [v64[i].data_ptr() for i in range(n)]
+        del stack, tdata, tvar
+    kd, dptr = _ptr_table(dptrs)
+    kv, vptr = (None, None) if vptrs is None else _ptr_table(vptrs)
     stream = torch.cuda.current_stream(dev).cuda_stream
     times = []
     for it in range(args.warmup + args.steps):
         valid = np.zeros(n, dtype=np.intc)
         select = np.zeros(n, dtype=np.intc)
         if args.median:
-            rc = ctools.mpdaf_b200_median_arrays(n, dptr, 4, nvox, DEVICE, 0, out.data_ptr(), expmap.data_ptr(),
+            rc = ctools.mpdaf_b200_median_arrays(n, dptr, esz, nvox, DEVICE, 0, out.data_ptr(), expmap.data_ptr(),
                                                  valid, stream)
         else:
             rc = ctools.mpdaf_b200_sigma_clipping_arrays(
-                n, dptr, vptr, 4, nvox, DEVICE, 0, out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(),
+                n, dptr, vptr, esz, nvox, DEVICE, 0, out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(),
                 scales.ctypes.data, offsets.ctypes.data, select, valid, 2, args.nclip, args.nclip, 2, typ,
                 int(args.mad), stream)
         check(rc, "combine")
@@ -65,7 +79,7 @@ def main():
             times.append(ctools.mpdaf_b200_last_kernel_ms())
     ms = float(np.mean(times))
     a = 2 if (typ == 0 and not args.median) else 1
-    bpv = n * 4 * a + (12 if args.median else 20)
+    bpv = n * esz * a + (12 if args.median else 20)
     res = dict(kernel=ctools.mpdaf_b200_last_kernel_name().decode(), n=n, nz=nz, ms=ms,
                gvox_exp_s=n * nvox / ms / 1e6, gbs=bpv * nvox / ms / 1e6, bytes_per_voxel=bpv,
                rejected=int(valid.sum() - select.sum()) if not args.median else None,
