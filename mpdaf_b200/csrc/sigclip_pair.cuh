@@ -59,38 +59,39 @@ template <> struct Vec2<double> { using type = double2; };
 template <int NB, int ES = 4>
 struct PairCfg {
     static constexpr int stage_bytes = NB * 64 * ES;   // one [NB][64] tile of float32 (ES = 4) or float64 (8) samples
-    static constexpr int col_pad = 5;                  // guard rows below (-inf) and above (+inf) the sorted column: the
-                                                       // clip loop probes up to five ranks beyond either end without clamps
-    static constexpr int col_rows = NB + 2 * col_pad;
-    static constexpr int col_bytes = col_rows * 32 * 4;   // sorted packed keys of one warp
+    static constexpr int col_bytes = NB * 32 * 4;      // sorted packed keys of one warp
     static constexpr int misc_bytes = 4096;            // barriers, reciprocal table, per-exposure constants
     static constexpr int budget = 227 * 1024 - misc_bytes;
-    // consumer warps: bounded by the register file (about 2 NB + 72 registers per thread: sorted and unsorted packed
-    // keys plus the per-voxel state), by 15 (four warps per scheduler with the producer), and by shared memory
-    static constexpr int c_regs = 2048 / (2 * NB + 72) - 1;
-    static constexpr int c_smem = budget / (stage_bytes + col_bytes);     // a stage is held for the whole tile: one per consumer
-    static constexpr int c_auto = c_regs < 15 ? (c_regs < c_smem ? c_regs : c_smem) : (15 < c_smem ? 15 : c_smem);
+    // Every warp of the block is a consumer that owns its stage(s) and refills them itself (no producer warp: with 168
+    // registers per thread the register file holds exactly 12 warps, three per scheduler).  Their number is bounded
+    // by the register file (about 2 NB + 72 registers per thread: sorted and unsorted packed keys plus the per-voxel
+    // state), by 16 (four warps per scheduler), and by shared memory (a stage is held until the clip loop is over).
+    static constexpr int c_regs = 2048 / (2 * NB + 72);
+    static constexpr int c_smem = budget / (stage_bytes + col_bytes);
+    static constexpr int c_cap = c_regs < 16 ? c_regs : 16;
+    static constexpr int c_fit = c_cap < c_smem ? c_cap : c_smem;
+    // the warps of a block run in phase (round barrier): 4 k + 1 of them leave three schedulers waiting for the fourth's
+    // extra warp in every round (N = 64 without STAT: 8 warps 0.688 ms, 9 warps 0.785 ms)
+    static constexpr int c_auto = (c_fit > 4 && c_fit % 4 == 1) ? c_fit - 1 : c_fit;
     static constexpr int C = MB_PAIR_CONSUMERS ? MB_PAIR_CONSUMERS : c_auto;
-        // The ring length is a multiple of C: stage s is then only ever consumed by warp s % C, in order.  (An mbarrier
-    // wait only knows the PARITY of the phase it waits for; with an arbitrary ring length a warp that runs two uses
-    // of a stage ahead of another would see the earlier phase of equal parity completed and read a stale tile.)
-    static constexpr int st_fit = (budget - C * col_bytes) / stage_bytes;
-    static constexpr int ST = (st_fit / C > 2 ? 2 : st_fit / C) * C;
-    static constexpr int threads = (C + 1) * 32;       // consumers + one producer warp
-    static_assert(C >= 2 && ST >= C, "stack too deep for the pair kernel");
+    // stages per warp: two where shared memory allows (the next tile is then requested a whole tile ahead)
+    static constexpr int SPW = (budget - C * col_bytes) / (C * stage_bytes) >= 2 ? 2 : 1;
+    static constexpr int ST = SPW * C;
+    static constexpr int threads = C * 32;
+    static_assert(C >= 2, "stack too deep for the pair kernel");
 };
 
 template <int NB, typename ET = float>
 struct PairSmem {
-    ET stage[PairCfg<NB, sizeof(ET)>::ST][NB][64];        // DATA tiles
-    unsigned col[PairCfg<NB, sizeof(ET)>::C][PairCfg<NB, sizeof(ET)>::col_rows][32];   // guard rows + sorted keys: low half voxel 2l, high half voxel 2l+1
+    ET stage[PairCfg<NB, sizeof(ET)>::ST][NB][64];        // DATA tiles: stages w * SPW .. w * SPW + SPW - 1 belong to warp w
+    unsigned col[PairCfg<NB, sizeof(ET)>::C][NB][32];     // sorted keys: low half voxel 2l, high half voxel 2l+1
     double rcp[NB + 1];
     double2 os[NB];                                       // (offset, scale) for lane-dependent lookups
-    float2 kso[NB];                                       // float32 (scale, offset * scale), likewise
     double osp[NB];                                       // offset * scale exactly as pass 1 uses it
-    unsigned long long full[PairCfg<NB, sizeof(ET)>::ST];    // TMA completion of a stage's DATA tile
-    unsigned long long empty[PairCfg<NB, sizeof(ET)>::ST];   // consumer has finished with the stage
+    unsigned long long full[PairCfg<NB, sizeof(ET)>::ST]; // TMA completion of a stage's DATA tile
+    unsigned pad[64];                                     // the clip loop may read up to five rows beyond the last column
 };
+static_assert(sizeof(PairSmem<48, float>) <= 227 * 1024 && sizeof(PairSmem<64, float>) <= 227 * 1024 && sizeof(PairSmem<48, double>) <= 227 * 1024, "shared memory");
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
@@ -371,37 +372,14 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
     for (int i = tid; i <= NB; i += Cfg::threads) sm.rcp[i] = i > 0 ? 1.0 / (double)i : 0.0;
     for (int i = tid; i < NB; i += Cfg::threads) {
         sm.os[i] = S.os[i];
-        sm.kso[i] = make_float2(S.kscale[i], S.koffset[i]);
         sm.osp[i] = S.osp[i];
     }
-    for (int i = tid; i < C * 2 * Cfg::col_pad * 32; i += Cfg::threads) {
-        const int w = i / (2 * Cfg::col_pad * 32), r = (i / 32) % (2 * Cfg::col_pad), l = i & 31;
-        if (r < Cfg::col_pad) sm.col[w][r][l] = 0xFF80FF80u;                           // (-inf, -inf)
-        else sm.col[w][NB + r][l] = 0x7F807F80u;                                       // (+inf, +inf)
-    }
     if (tid == 0) {
-        for (int s = 0; s < ST; s++) {
-            mbar_init(&sm.full[s], 1);
-            mbar_init(&sm.empty[s], 1);
-        }
+        for (int s = 0; s < ST; s++) mbar_init(&sm.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();   // the only block-wide barrier
-
-    // ---- producer warp: one lane keeps the ring full -------------------------------------------------
-    if (warp == C) {
-        if (lane == 0) {
-            long long tile = blockIdx.x;
-            for (unsigned k = 0; tile < ntiles; k++, tile += gridDim.x) {
-                const unsigned st = k % ST, ph = (k / ST) & 1u;
-                mbar_wait_relaxed(smem_u32(&sm.empty[0]) + 8u * st, ph ^ 1u);   // a fresh barrier passes the wait on parity 1
-                mbar_expect_tx(&sm.full[st], kTileBytes);
-                tma_load_2d(&sm.stage[st][0][0], &M.data, (int)(tile << 6), 0, &sm.full[st]);
-            }
-        }
-        return;
-    }
 
     // ---- consumer warps -------------------------------------------------------------------------------
     const int c = warp;
@@ -411,7 +389,10 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
 #pragma unroll
     for (int k = 0; k < W; k++) { cnt_inval[k] = 0u; cnt_drop[k] = 0u; }
     unsigned tiles_done = 0;
-    const unsigned short* colh = reinterpret_cast<const unsigned short*>(&sm.col[c][Cfg::col_pad][lane]);   // key q of voxel h: colh[q * 64 + h], q in -5 .. NB + 4
+    // key q of voxel h: colh[q * 64 + h].  The clip loop also reads up to five ranks beyond either end of the column
+    // (the neighbouring warp's column, the stage before or the tables behind the array): whatever it finds there can
+    // only add candidates beyond the window's own keys, which sends the voxel to the exact kernel.
+    const unsigned short* colh = reinterpret_cast<const unsigned short*>(&sm.col[c][0][lane]);
     auto col16 = [&](int q, int h) -> unsigned { return (unsigned)colh[q * 64 + h]; };
     auto keyf = [&](int q, int h) -> float { return __uint_as_float(col16(q, h) << 16); };
     const float nlo32 = (float)A.nclip_low, nup32 = (float)A.nclip_up;
@@ -421,8 +402,26 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
     // rounds of C tiles; the trip count is uniform over the consumer warps so that the round barrier is legal
     const long long my_tiles = ntiles > (long long)blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const long long rounds = (my_tiles + C - 1) / C;
+    // this warp's tiles: the c-th of every round; its j-th tile uses stage c * SPW + j % SPW.  Request the first SPW tiles.
+    auto request_tile = [&](long long j) {      // lane 0 only
+        const long long kk = j * C + c;
+        if (kk >= my_tiles) return;
+        const unsigned st = (unsigned)(c * Cfg::SPW + (int)(j % Cfg::SPW));
+        mbar_expect_tx(&sm.full[st], kTileBytes);
+        tma_load_2d(&sm.stage[st][0][0], &M.data, (int)(((long long)blockIdx.x + kk * gridDim.x) << 6), 0, &sm.full[st]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < Cfg::SPW; j++) request_tile(j);
+    }
     for (long long r = 0; r < rounds; r++) {
-        if (flags & 2) {
+        if (flags >> 4) {
+            // tuning: flags >> 4 groups of consecutive warps, each phase-locked on its own barrier
+            const int ng = flags >> 4, base = C / ng, rem = C % ng;
+            const int g = c < rem * (base + 1) ? c / (base + 1) : rem + (c - rem * (base + 1)) / (base > 0 ? base : 1);
+            const int cnt = (g < rem ? base + 1 : base) * 32;
+            asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(cnt) : "memory");
+        } else if (flags & 2) {
             // default: two groups of consumer warps, each phase-locked on its own barrier and free to drift against the
             // other (measured 0 .. 3 % over one group: while one group sorts on the ALU pipe the other can be in pass 1)
             constexpr int G0 = (C + 1) / 2, G1 = C - G0;
@@ -431,9 +430,8 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         } else if (flags & 1) asm volatile("bar.sync 1, %0;" ::"n"(C * 32) : "memory");
         const long long kk64 = r * C + c;
         if (kk64 >= my_tiles) continue;
-        const unsigned k = (unsigned)kk64;
         const long long tile = (long long)blockIdx.x + kk64 * gridDim.x;
-        const unsigned st = k % ST, ph = (k / ST) & 1u;
+        const unsigned st = (unsigned)(c * Cfg::SPW + (int)(r % Cfg::SPW)), ph = (unsigned)(r / Cfg::SPW) & 1u;
         ET (*dt)[64] = sm.stage[st];
         const long long v0 = (tile << 6) + 2 * lane;            // this lane's voxels: v0, v0 + 1
         // the STAT rows of these voxels are read at the end of the tile: start them on their way into L2 now
@@ -531,7 +529,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         // ---- order the packed keys; sorted column to shared memory ------------------------------------------
         sort_pairs<NB>(key);
 #pragma unroll
-        for (int q = 0; q < NB; q++) sm.col[c][Cfg::col_pad + q][lane] = key[q];
+        for (int q = 0; q < NB; q++) sm.col[c][q][lane] = key[q];
         __syncwarp();
 
         // ---- clip iterations (tools.c:82-118), both voxels in lockstep ---------------------------------------
@@ -740,38 +738,35 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 double dT1 = 0.0, dS2 = 0.0;
                 int rl = 0, rh = 0;
                 bool unc = false;
-                float kmax_rl = -CUDART_INF_F, kmin_kl = CUDART_INF_F, kmin_rh = CUDART_INF_F, kmax_kh = -CUDART_INF_F;
-                ExpSet<NB> nr;
-#pragma unroll
-                for (int kk = 0; kk < W; kk++) {
-                    unsigned mw = RL[h][kk] | RH[h][kk];
-                    while (mw) {
-                        const int i = 32 * kk + (__ffs(mw) - 1);
-                        mw &= mw - 1u;
-                        const bool low = (RL[h][kk] >> (i & 31)) & 1u;
-                        const ET dval = dt[i][2 * lane + h];
-                        const double2 osj = sm.os[i];
-                        const float2 ksj = sm.kso[i];
-                        const double t = UNIT ? (double)dval - p[h] : __fma_rn((double)dval, osj.y, sm.osp[i] - p[h]);
-                        const float t32 = F64 ? __double2float_rn(t) : (UNIT ? (float)dval - pf[h] : __fmaf_rn((float)dval, ksj.x, ksj.y) - pf[h]);
-                        unsigned kb;
-                        asm("cvt.rn.bf16x2.f32 %0, %1, %1;" : "=r"(kb) : "f"(t32));
-                        const float tk = __uint_as_float(kb & 0xFFFF0000u);          // this sample's key, as in pass 1
-                        const double diff = t - (low ? clo_d : cup_d);
-                        unc = unc || !(fabs(diff) > tb_d);
-                        const bool out = low ? (diff <= 0.0) : (diff >= 0.0);        // strict window, tools.c:95
-                        if (out) {
-                            dT1 += t;
-                            dS2 += t * t;
-                            nr.w[kk] |= 1u << (i & 31);
-                            if (low) { rl++; kmax_rl = fmaxf(kmax_rl, tk); } else { rh++; kmin_rh = fminf(kmin_rh, tk); }
-                        } else {
-                            if (low) kmin_kl = fminf(kmin_kl, tk); else kmax_kh = fmaxf(kmax_kh, tk);
-                        }
+                unsigned long long nr = 0ull;                                        // candidates rejected by this evaluation
+                // one loop over the candidates of all mask words (W <= 2: a 64-bit mask)
+                unsigned long long mw = (unsigned long long)(RL[h][0] | RH[h][0]), lowm = (unsigned long long)RL[h][0];
+                if constexpr (W > 1) {
+                    mw |= (unsigned long long)(RL[h][W - 1] | RH[h][W - 1]) << 32;
+                    lowm |= (unsigned long long)RL[h][W - 1] << 32;
+                }
+                while (mw) {
+                    const int i = __ffsll((long long)mw) - 1;
+                    const unsigned long long rest = mw & (mw - 1ull), bit = mw ^ rest;
+                    mw = rest;
+                    const bool low = (lowm >> i) & 1ull;
+                    const ET dval = dt[i][2 * lane + h];
+                    const double t = UNIT ? (double)dval - p[h] : __fma_rn((double)dval, sm.os[i].y, sm.osp[i] - p[h]);
+                    const double diff = t - (low ? clo_d : cup_d);
+                    unc = unc || !(fabs(diff) > tb_d);
+                    const bool out = low ? (diff <= 0.0) : (diff >= 0.0);            // strict window, tools.c:95
+                    if (out) {
+                        dT1 += t;
+                        dS2 += t * t;
+                        nr |= bit;
+                        if (low) rl++; else rh++;
                     }
                 }
-                // undecidable sample, or rejected and kept candidates not separated in key order (the window is kept by key rank)
-                if (unc || kmax_rl > kmin_kl || kmin_rh < kmax_kh) { slow[h] = done[h] = true; continue; }
+                // An undecidable sample sends the voxel to the exact kernel.  Otherwise every rejected candidate lies more than
+                // Tb beyond its bound and every kept one more than Tb inside: their float32 key values (each within
+                // 2^-22 |t| + E0 of t, and Tb >= 2^-19 |bound| + E0) are ordered the same way, so the rejected candidates hold
+                // the outermost ranks of the sorted column and the surviving window is again a contiguous range of ranks.
+                if (unc) { slow[h] = done[h] = true; continue; }
                 const int m = b[h] - a[h];
                 const int ni = m - rl - rh;
                 if (ni < nstop || ni == m) { done[h] = true; continue; }             // tools.c:100-103
@@ -779,17 +774,16 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 T1[h] -= dT1;
                 S2[h] -= dS2;
 #pragma unroll
-                for (int kk = 0; kk < W; kk++) {
-                    rej[h].w[kk] |= nr.w[kk];
-                }
+                for (int kk = 0; kk < W; kk++) rej[h].w[kk] |= (unsigned)(nr >> (kk ? 32 : 0));
                 a[h] += rl;
                 b[h] -= rh;
                 if (itl[h] <= 0) final_stats(h);                                     // no clip left: these statistics stand
             }
         }
-        // ---- the samples are consumed: hand the stage back to the producer --------------------------------------
+        // ---- the samples are consumed: request the tile that uses this stage next ---------------------------------
+        // (the warp's own reads of the stage are complete: no other warp ever touches it)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[st]);
+        if (lane == 0) request_tile(r + Cfg::SPW);
 
         // ---- results of the two voxels ------------------------------------------------------------------------
         int kept[2];
@@ -811,10 +805,22 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         // half-batches; float32 FMAs in chains of <= 3 terms, chains summed in float64: <= 4 * 2^-24 relative for
         // non-negative STAT.  A sign bit among the loaded values (a negative or negative-NaN STAT, kept or not)
         // sends the lane to float64 products in exposure order.
+        // ---- per-exposure counters: transpose the lanes' masks, one POPC per lane ----------------------------------
+        auto count_tile = [&]() {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int kk = 0; kk < W; kk++) {
+                    cnt_inval[kk] += __popc(tc.apply(inval[h].w[kk]));
+                    cnt_drop[kk] += __popc(tc.apply(drop[h].w[kk]));
+                }
+            }
+            tiles_done++;
+        };
+        bool counted = false;
         double vsum[2] = {0.0, 0.0};
         if constexpr (PROP) {
             constexpr int NACC = (NB + 2) / 3;
-            constexpr int HB = NB / 2;
             float vacc[2][NACC];
 #pragma unroll
             for (int j = 0; j < NACC; j++) { vacc[0][j] = 0.f; vacc[1][j] = 0.f; }
@@ -848,17 +854,13 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                 const float* vp = static_cast<const float*>(S.var0) + v0;
                 float2 sv[NB];
 #pragma unroll
-                for (int i = 0; i < HB; i++) {
+                for (int i = 0; i < NB; i++) {
                     asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
                     vp += S.vstride;
                 }
                 asm volatile("" ::: "memory");
-#pragma unroll
-                for (int i = HB; i < NB; i++) {
-                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
-                    vp += S.vstride;
-                }
-                asm volatile("" ::: "memory");
+                count_tile();                     // the counter transposes run while the STAT rows are on their way
+                counted = true;
 #pragma unroll
                 for (int i = 0; i < NB; i++) {
                     if (!drop[0].test(i)) vacc[0][i % NACC] = __fmaf_rn(sv[i].x, S.scale2f[i], vacc[0][i % NACC]);
@@ -881,16 +883,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             }
         }
 
-        // ---- per-exposure counters: transpose the lanes' masks, one POPC per lane ----------------------------------
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-#pragma unroll
-            for (int kk = 0; kk < W; kk++) {
-                cnt_inval[kk] += __popc(tc.apply(inval[h].w[kk]));
-                cnt_drop[kk] += __popc(tc.apply(drop[h].w[kk]));
-            }
-        }
-        tiles_done++;
+        if (!counted) count_tile();
 
         // ---- stores ---------------------------------------------------------------------------------------------
         double ov[2];
