@@ -156,14 +156,15 @@ int launch_generic(const Job& j, int device, cudaStream_t stream)
                              (const StackTable*)j.table_dev, j.a);
 }
 
-int enqueue_combine_only(const Job& j, int device, cudaStream_t stream);
+int enqueue_combine_only(const Job& j, int device, cudaStream_t stream, bool* hist_fused = nullptr);
 
 // Enqueue the combination of one device-resident stack (or slab) on `stream`, followed by the
 // exposure-map histogram of that slab (expnb without a host pass).
 int enqueue_combine(const Job& j, int device, cudaStream_t stream)
 {
-    const int rc = enqueue_combine_only(j, device, stream);
-    if (rc != MPDAF_B200_OK || !g_hist_enabled || j.a.nvox <= 0) return rc;
+    bool fused = false;      // the pair kernels count the exposure map themselves
+    const int rc = enqueue_combine_only(j, device, stream, &fused);
+    if (rc != MPDAF_B200_OK || !g_hist_enabled || j.a.nvox <= 0 || fused) return rc;
     const int grid = (int)std::min<long long>((j.a.nvox + 255) / 256, (long long)g_dev[device].sm_count * 8);
     expmap_hist_kernel<<<grid, 256, 0, stream>>>(j.a.expmap, j.a.nvox, g_dev[device].hist);
     MB_CUDA(cudaGetLastError());
@@ -171,8 +172,9 @@ int enqueue_combine(const Job& j, int device, cudaStream_t stream)
     return MPDAF_B200_OK;
 }
 
-int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
+int enqueue_combine_only(const Job& j, int device, cudaStream_t stream, bool* hist_fused)
 {
+    unsigned long long* const hist = (hist_fused != nullptr && g_hist_enabled) ? g_dev[device].hist : nullptr;
     bool unit = true;
     for (int i = 0; i < j.nfiles; i++) {
         if (j.scale && j.scale[i] != 1.0) unit = false;
@@ -194,6 +196,7 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         ctx.stream = stream;
         ctx.name = name;
         ctx.name_len = sizeof name;
+        ctx.hist = hist;
         int rc = MPDAF_B200_ERR_ARG;
         switch (nb) {
 #define MB_CASE(NB) case NB: rc = j.median ? mb_launch_median_warp_##NB(j, ctx) : mb_launch_warp_##NB(j, unit, ctx); break;
@@ -202,6 +205,7 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         }
         g_last_kernel = name;
         g_last_launches += ctx.launches;
+        if (hist_fused != nullptr) *hist_fused = ctx.hist_fused && rc == MPDAF_B200_OK;
         return rc;
     }
     // 129..512 float32 exposures, plain sigma clip: R sorted runs of 64 (sigclip_runs.cuh)
@@ -238,12 +242,14 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream)
         ctx.stream = stream;
         ctx.name = name;
         ctx.name_len = sizeof name;
+        ctx.hist = hist;
         bool taken = false;
         const int rc = j.nfiles <= 12 ? mb_launch_pair64_12(j, unit, ctx, taken)
                      : j.nfiles <= 24 ? mb_launch_pair64_24(j, unit, ctx, taken) : mb_launch_pair64_48(j, unit, ctx, taken);
         if (rc != MPDAF_B200_OK || taken) {
             g_last_kernel = name;
             g_last_launches += ctx.launches;
+            if (hist_fused != nullptr) *hist_fused = ctx.hist_fused && rc == MPDAF_B200_OK;
             return rc;
         }
     }

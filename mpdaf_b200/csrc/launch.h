@@ -37,6 +37,8 @@ struct LaunchCtx {
     char* name = nullptr;                // receives the kernel family name
     size_t name_len = 0;
     int launches = 0;                    // incremented per kernel launch
+    unsigned long long* hist = nullptr;  // device exposure-map histogram a kernel may add to itself (null: not wanted)
+    bool hist_fused = false;             // set by a launcher whose kernels filled `hist`: no separate histogram pass
 };
 
 int fail(int code, const std::string& msg);   // records the message (ctools_abi.cu)

@@ -50,6 +50,7 @@ struct PairArgs {
     float scale2f[NB];                     // float32(scale^2)
     double scale2[NB];
     double osmax;                          // max |offset * scale|: part of the absolute key error
+    unsigned long long* hist;              // exposure-map histogram [>= NB + 1] the kernels add to (null: not wanted)
 };
 
 template <typename ET> struct Vec2;
@@ -89,6 +90,7 @@ struct PairSmem {
     double2 os[NB];                                       // (offset, scale) for lane-dependent lookups
     double osp[NB];                                       // offset * scale exactly as pass 1 uses it
     unsigned long long full[PairCfg<NB, sizeof(ET)>::ST]; // TMA completion of a stage's DATA tile
+    unsigned hist[NB + 1];                                // voxels of this block by number of exposures kept
     unsigned pad[64];                                     // the clip loop may read up to five rows beyond the last column
 };
 static_assert(sizeof(PairSmem<48, float>) <= 227 * 1024 && sizeof(PairSmem<64, float>) <= 227 * 1024 && sizeof(PairSmem<48, double>) <= 227 * 1024, "shared memory");
@@ -168,6 +170,7 @@ __device__ __noinline__ void exact_voxel_store(const PairArgs<NB>& S, const Clip
     A.out[v] = mean;
     A.outvar[v] = ov;
     A.expmap[v] = kept;
+    if (S.hist != nullptr) atomicAdd(S.hist + kept, 1ull);
 }
 
 // Queued voxels: the reference algorithm restated literally (merging.c:423-477, tools.c:9-24, :39-51, :82-118), one
@@ -318,6 +321,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
             A.out[v] = mean;
             A.outvar[v] = ov;
             A.expmap[v] = kept;
+            if (S.hist != nullptr) atomicAdd(S.hist + kept, 1ull);
         }
         __syncwarp();
     }
@@ -374,6 +378,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         sm.os[i] = S.os[i];
         sm.osp[i] = S.osp[i];
     }
+    for (int i = tid; i <= NB; i += Cfg::threads) sm.hist[i] = 0u;
     if (tid == 0) {
         for (int s = 0; s < ST; s++) mbar_init(&sm.full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -415,9 +420,11 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         for (int j = 0; j < Cfg::SPW; j++) request_tile(j);
     }
     for (long long r = 0; r < rounds; r++) {
-        if (flags >> 4) {
+        if ((r & ((flags >> 8) & 15)) != 0) {
+            // tuning: flags bits 8..11 = mask; rounds with (r & mask) != 0 run without the phase lock
+        } else if ((flags >> 4) & 15) {
             // tuning: flags >> 4 groups of consecutive warps, each phase-locked on its own barrier
-            const int ng = flags >> 4, base = C / ng, rem = C % ng;
+            const int ng = (flags >> 4) & 15, base = C / ng, rem = C % ng;
             const int g = c < rem * (base + 1) ? c / (base + 1) : rem + (c - rem * (base + 1)) / (base > 0 ? base : 1);
             const int cnt = (g < rem ? base + 1 : base) * 32;
             asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(cnt) : "memory");
@@ -886,15 +893,26 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
         if (!counted) count_tile();
 
         // ---- stores ---------------------------------------------------------------------------------------------
+        // (divisions by the small integers as multiplications by their correctly rounded reciprocals: <= 2 ulp)
         double ov[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
+            const double rk = sm.rcp[kept[h]];
             if (n[h] == 0) ov[h] = CUDART_NAN;
-            else if (PROP) ov[h] = vsum[h] / ((double)kept[h] * (double)kept[h]);           // merging.c:462
+            else if (PROP) ov[h] = vsum[h] * rk * rk;                                       // merging.c:462
             else if (kept[h] > 1) {
                 ov[h] = varl[h];                                                            // sigma^2, merging.c:465
-                if (A.typ_var == 1) ov[h] /= (double)(kept[h] - 1);                         // merging.c:467
+                if (A.typ_var == 1) ov[h] *= sm.rcp[kept[h] - 1];                           // merging.c:467
             } else ov[h] = CUDART_NAN;
+        }
+        // exposure-map histogram (expnb, cubelist.py:69-74): the lanes of a warp mostly share one value
+        if (S.hist != nullptr) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int val = (slow[h] || v0 + h >= A.nvox) ? -1 : kept[h];             // queued voxels are counted by the exact kernel
+                const unsigned peers = __match_any_sync(FULLM, val);
+                if (val >= 0 && lane == __ffs(peers) - 1) atomicAdd(&sm.hist[val], (unsigned)__popc(peers));
+            }
         }
         if (v0 + 1 < A.nvox && !slow[0] && !slow[1]) {
             *reinterpret_cast<double2*>(A.out + v0) = make_double2(mean[0], mean[1]);
@@ -927,6 +945,11 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt_inval[kk]));
             atomicAdd(A.select_cnt + e, (unsigned long long)(seen - cnt_drop[kk]));
         }
+    }
+    if (S.hist != nullptr) {
+        __syncthreads();      // every warp runs the same number of rounds and none has returned
+        for (int i = tid; i <= NB; i += Cfg::threads)
+            if (sm.hist[i]) atomicAdd(S.hist + i, (unsigned long long)sm.hist[i]);
     }
 }
 

@@ -97,9 +97,6 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
         // MAD: with var = 'propagate' only (sigma then feeds nothing but decisions; the 'stat' variances would need the
         // exact MAD of the last set and stay on the warp kernel, which is bit-identical to the reference there)
         if (j.a.mad && !need_var) return MPDAF_B200_OK;
-        // 49 .. 64 exposures with var = 'propagate': nine consumer warps and 128 unsorted-key registers leave the pair
-        // kernel behind the warp kernel (2290 vs 2580 GB/s at N = 64, profiles/r02_depth_sweep.txt); it still wins without STAT
-        if (NB > 48 && need_var && std::getenv("MPDAF_B200_PAIR_ALWAYS") == nullptr) return MPDAF_B200_OK;
         auto pitch_of = [&](const void* const* rows) -> unsigned long long {   // elements between rows, 0 = not equally pitched / unaligned
             if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
             if (j.nfiles == 1) return (unsigned long long)((j.a.nvox + 3) / 4 * 4);
@@ -136,6 +133,8 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             osmax = std::max(osmax, std::fabs(of * sc));
         }
         s.osmax = osmax;
+        s.hist = ctx.hist;
+        ctx.hist_fused = ctx.hist != nullptr;
         using Cfg = PairCfg<NB, sizeof(ET)>;
         std::snprintf(ctx.name, ctx.name_len, "sigclip_pair<%d,%s%s>", NB, unit ? "unit" : "scaled", F64 ? ",f64" : "");
         const long long ntiles = (j.a.nvox + 63) / 64;
@@ -144,7 +143,7 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             MB_CUDA(cudaMemsetAsync(ctx.slow_n, 0, sizeof(unsigned), ctx.stream));
             const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
-            static const int pair_flags = std::getenv("MPDAF_B200_PAIR_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_PAIR_FLAGS")) : 2;
+            static const int pair_flags = std::getenv("MPDAF_B200_PAIR_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_PAIR_FLAGS")) : (2 | 256);   // two phase-locked groups, re-aligned every second round
             kernel<<<grid, Cfg::threads, smem, ctx.stream>>>(s, j.a, ntiles, ctx.slow_q, ctx.slow_n, ctx.slow_cap, pair_flags, maps);
             MB_CUDA(cudaGetLastError());
             // queued voxels (uncertifiable from their keys): the reference algorithm restated literally, one thread each

@@ -110,10 +110,9 @@ def test_pair_kernel_means_within_1e_12(scaled):
             np.testing.assert_allclose(got["var"], want["var"], rtol=3e-7, atol=0, equal_nan=True)   # float32 chains of 3
 
 
-def test_pair_kernel_deep_bucket_with_stat(monkeypatch):
-    """49 .. 64 exposures with var = 'propagate' normally go to the warp kernel (faster there); the pair kernel's
-    instantiation stays correct and is kept covered through MPDAF_B200_PAIR_ALWAYS."""
-    monkeypatch.setenv("MPDAF_B200_PAIR_ALWAYS", "1")
+def test_pair_kernel_deep_bucket_with_stat():
+    """49 .. 64 exposures with var = 'propagate': the pair kernel (eight warps, each refilling its own stage) is the
+    dispatch's choice since the producer warp went (3591 vs 2602 GB/s of the warp kernel at N = 64)."""
     rng = np.random.default_rng(64)
     for n in (49, 64):
         data, var = random_stack(rng, n, (4, 9, 10), nan_frac=0.1, outlier_frac=0.05)
@@ -121,9 +120,6 @@ def test_pair_kernel_deep_bucket_with_stat(monkeypatch):
         got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
         assert "sigclip_pair<64" in cuda().kernel_name()
         assert_same_result(got, oracle.combine_port(data, var, **kw))
-    monkeypatch.delenv("MPDAF_B200_PAIR_ALWAYS")
-    got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
-    assert "sigclip_warp<64" in cuda().kernel_name()
 
 
 @pytest.mark.parametrize("nmax,lo,up,nstop", [(0, 2.0, 2.0, 2), (1, 1.5, 3.0, 1), (3, 1.0, 1.0, 3),

@@ -21,7 +21,6 @@ def main():
     import cuda_runner as cr
     from helpers import assert_same_result, random_stack
     oracle.build()
-    os.environ["MPDAF_B200_PAIR_ALWAYS"] = "1"    # also where the dispatch would prefer the warp kernel (49 .. 64 exposures with STAT)
     bad = 0
     cases = 0
     for n, ties in itertools.product([2, 3, 4, 5, 12, 24, 33, 48, 64], [False, True]):
