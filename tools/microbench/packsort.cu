@@ -36,6 +36,14 @@ __device__ __forceinline__ void ce(unsigned& a, unsigned& b)
     } else if constexpr (MODE == 5) {
         asm("min.u16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(b));
         asm("max.f16x2 %0, %1, %2;" : "=r"(hi) : "r"(a), "r"(b));
+    } else if constexpr (MODE == 7) {          // packed min + three-input XOR: max = a ^ b ^ min (bit patterns)
+        asm("min.bf16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(b));
+        asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(hi) : "r"(a), "r"(b), "r"(lo));
+    } else if constexpr (MODE == 8) {          // packed min + integer a + b - min (ptxas fuses the two adds into one IADD3)
+        unsigned t;
+        asm("min.bf16x2 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(b));
+        asm volatile("sub.u32 %0, %1, %2;" : "=r"(t) : "r"(a), "r"(lo));
+        asm volatile("add.u32 %0, %1, %2;" : "=r"(hi) : "r"(t), "r"(b));
     } else {
         asm("min.f32 %0, %1, %2;" : "=r"(lo) : "r"(a), "r"(b));
         asm("max.f32 %0, %1, %2;" : "=r"(hi) : "r"(a), "r"(b));
@@ -215,7 +223,14 @@ int main()
     run_sort<3, 768, 1>("f16x2 HMNMX2", sms, 2);
     run_sort<4, 768, 1>("u16x2 VIMNMX", sms, 2);
     run_sort<5, 768, 1>("VIMNMX min + HMNMX2 max", sms, 2);
+    run_sort<7, 768, 1>("bf16x2 HMNMX2 + LOP3", sms, 2);
+    run_sort<8, 768, 1>("bf16x2 HMNMX2 + IADD3", sms, 2);
+    printf("-- 12 warps/SM (384 threads) --\n");
+    run_sort<2, 384, 1>("bf16x2 HMNMX2", sms, 2);
+    run_sort<7, 384, 1>("bf16x2 HMNMX2 + LOP3", sms, 2);
+    run_sort<8, 384, 1>("bf16x2 HMNMX2 + IADD3", sms, 2);
     printf("-- same, 8 warps/SM (256 threads) --\n");
+    run_sort<7, 256, 1>("bf16x2 HMNMX2 + LOP3", sms, 2);
     run_sort<2, 256, 1>("bf16x2 HMNMX2", sms, 2);
     run_sort<4, 256, 1>("u16x2 VIMNMX", sms, 2);
     run_sort<5, 256, 1>("VIMNMX min + HMNMX2 max", sms, 2);
