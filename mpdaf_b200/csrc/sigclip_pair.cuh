@@ -1,5 +1,5 @@
 // Pair-packed, TMA-pipelined sigma-clip kernel for sm_100a: the main combine kernel of round 2
-// (float32 stacks up to 64 deep whose rows are equally pitched and 16-byte aligned).
+// (float32 stacks up to 64 deep, float64 stacks up to 48 deep, rows equally pitched and 16-byte aligned).
 //
 // Reference behaviour restated (never copied): src/merging.c:423-477 (gather, n == 0 / 1, outputs,
 // counters) and src/tools.c:82-118 (median-centred iterative clip, strict window, stop rules).
@@ -11,19 +11,24 @@
 //  * a lane owns TWO neighbouring voxels and their 16-bit keys share a register, so one HMNMX2.BF16 min plus
 //    one max performs the compare-exchange of both voxels: half the sort instructions per voxel;
 //  * the keys are bfloat16(w - pivot) with no exposure index.  Which exposures fall outside the clip window is
-//    recovered afterwards by ONE packed comparison pass (2 HSETP2 per exposure for both voxels) of the unsorted
-//    keys, kept in registers, against the window's boundary keys -- and only when something is rejected;
-//  * a producer warp streams [NB][64] tiles into a ring of shared-memory stages with cp.async.bulk.tensor
-//    (TMA, mbarrier completion); consumer warps never wait on a load they issued themselves, and the STAT tile
-//    of a voxel pair lands in the stage its DATA tile occupied, while the sort and the clip loop run;
-//  * dropped samples (invalid or rejected) are zeroed in the staged STAT tile, so the propagated variance is an
-//    unpredicated FFMA stream; pass 1 is predicated PTX (one FSETP per sample, no selects, no branches).
+//    recovered afterwards by ONE packed comparison pass (one HSETP2 per exposure and side for both voxels) of the
+//    unsorted keys, kept in registers, against the window's boundary keys -- and only when something is rejected;
+//  * every warp owns one (or two) shared-memory stages and keeps them filled itself: lane 0 requests the [NB][64]
+//    tile of the warp's next-but-one round with cp.async.bulk.tensor (TMA, mbarrier completion) as soon as the
+//    clip loop has released the stage; the load lands while the warp computes the variance and stores.  There is
+//    no producer warp: at 168 registers per thread the register file holds exactly twelve warps (N = 48), three
+//    per scheduler, and all of them compute;
+//  * STAT rows (var = 'propagate') are read straight from L2 at the end of the tile (one TMA prefetch per tile
+//    at its start) into the registers the keys vacated;
+//  * the clip step is branch-free per voxel pair (both voxels' chains interleave), probes the ranks next to the
+//    window's ends without clamps, and ends a voxel as soon as no clip is left.
 // Decisions stay CERTIFIED: a key differs from its sample's w - pivot by at most KREL * |key| + E0, an order
 // statistic of the keys from the same order statistic of the samples by the same bound (both maps are
 // monotone), and sigma comes from float64 shifted moments (2^-28 relative, conditioning checked).  A voxel is
-// classified from its keys only if no key lies within that uncertainty of a clip bound; every other voxel goes
+// classified from its keys only if no key lies within that uncertainty of a clip bound; the few keys outside
+// the certain zone are candidates whose exact float64 values decide; a voxel with an undecidable candidate goes
 // to a queue and is recomputed by the reference algorithm restated literally (sigclip_pair_slow_kernel: one
-// thread per queued voxel, full warps instead of one slow lane stalling 63 fast ones).  expmap and the
+// WARP per queued voxel, full warps instead of one slow lane stalling 63 fast ones).  expmap and the
 // per-exposure counters are therefore bit-exact, means and variances within ~1e-15 / 3e-7 relative.
 #pragma once
 
@@ -98,18 +103,6 @@ static_assert(sizeof(PairSmem<48, float>) <= 227 * 1024 && sizeof(PairSmem<64, f
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// producer-side wait: the thread may be suspended up to the hint (ns) per try instead of spinning on the issue port
-__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar_addr, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITR_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@p bra DONER_%=;\n\t"
-        "bra WAITR_%=;\n\t"
-        "DONER_%=:\n\t}" ::"r"(bar_addr), "r"(parity), "r"(20000u) : "memory");
 }
 
 // key error model: bfloat16 rounding of t32 (2^-8 relative) + float32 evaluation of w - pivot
@@ -349,11 +342,12 @@ __device__ __forceinline__ void sort_pairs(unsigned (&a)[NB])
 #undef MB_CE
 }
 
-// Grid: one block per SM (persistent).  Block: PairCfg<NB>::C consumer warps + 1 producer warp.
-// Tiles of 64 consecutive voxels; block b takes tiles b, b + grid, b + 2 grid, ...; its k-th tile uses
-// ring stage k % ST and is processed by consumer warp k % C.  flags & 1: the consumer warps start every
-// round of C tiles together (named barrier), so that a line of the long straight-line loop body is fetched
-// once per SM and round instead of once per warp.
+// Grid: one block per SM (persistent).  Block: PairCfg<NB>::C warps, all of them consumers.
+// Tiles of 64 consecutive voxels; block b takes tiles b, b + grid, b + 2 grid, ...; its k-th tile is
+// processed by warp k % C in that warp's own stage.  flags & 2 (default): the warps start their rounds of C
+// tiles together in two groups (named barriers), so that a line of the long straight-line loop body is
+// fetched once per SM and round instead of once per warp; flags bits 8..11: rounds that skip the barrier
+// (default 1: re-aligned every second round); flags bits 4..7: number of groups (tuning).
 template <int NB, bool UNIT, bool PROP, bool MAD = false, typename ET = float>
 __global__ void __launch_bounds__(PairCfg<NB, sizeof(ET)>::threads, 1)
 sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntiles, unsigned* __restrict__ slow_q,

@@ -33,9 +33,39 @@ __device__ __forceinline__ const float* ld_row(const float* const* rows, int e)
     return reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(rows) + e));
 }
 
-template <int R, bool UNIT>
-__global__ void __launch_bounds__(32)
-sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsigned long long* slow_total)
+// Row pointers: from the device table (any layout), or base + e * stride when the rows are equally spaced (STRIDED).
+// The table lookup puts a dependent L2 round trip in front of every sample load (shared memory leaves the L1 too
+// small to keep the table): 64 serialized lookups per run, 0.05 of the HBM peak; the strided form has none.
+struct RunRows {
+    const float* data0;
+    const float* var0;
+    unsigned long long dstride, vstride;   // elements between consecutive rows
+    unsigned* next_tile;                   // device counter (zeroed before the launch): tiles are handed out dynamically,
+                                           // a warp held up by an exact-fallback voxel simply takes fewer of them
+    long long* phase_clk;                  // tuning: per-phase clock totals (null in production)
+};
+
+// Per-exposure constants in the kernel's parameter space (constant bank): a lookup in the device table costs an L2
+// round trip in front of every dependent use (measured: 33 % of the kernel on the scale^2 lookups of the variance sum).
+template <int NB>
+struct RunConsts {
+    double scale[NB], offset[NB], scale2[NB];
+};
+
+// warps per block: each warp owns R sorted columns of 8 KB; the block shares one copy of the per-exposure constants
+template <int R>
+struct RunsCfg {
+    static constexpr int NB = R * 64;
+    static constexpr int col_bytes = R * 64 * 32 * 4;
+    static constexpr int const_bytes = NB * 3 * 8;
+    static constexpr int WPB = (227 * 1024 - const_bytes) / col_bytes;
+    static constexpr int smem = WPB * col_bytes + const_bytes;
+};
+
+template <int R, bool UNIT, bool STRIDED = false>
+__global__ void __launch_bounds__(32 * RunsCfg<R>::WPB)
+sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsigned long long* slow_total, const RunRows RR,
+                    const __grid_constant__ RunConsts<R * 64> K)
 {
     constexpr int H = 64;
     constexpr int NB = R * H;
@@ -43,13 +73,25 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
     constexpr unsigned IDX = 511u;            // 9-bit exposure index in the key
     constexpr double KEPS = 0x1p-12;          // 4x the key resolution 2^-14
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float (*sk)[H][32] = reinterpret_cast<float (*)[H][32]>(smem_raw);   // sk[r][q][lane]
+    float (*sk)[H][32] = reinterpret_cast<float (*)[H][32]>(smem_raw + (threadIdx.x >> 5) * RunsCfg<R>::col_bytes);   // sk[r][q][lane], this warp's
+    // per-exposure constants: shared memory (the constant bank serves a run-dependent index at ~100 cycles per lookup)
+    double* const c_scale = reinterpret_cast<double*>(smem_raw + RunsCfg<R>::WPB * RunsCfg<R>::col_bytes);
+    double* const c_offset = c_scale + NB;
+    double* const c_scale2 = c_offset + NB;
+    for (int i = threadIdx.x; i < NB; i += blockDim.x) {
+        c_scale[i] = K.scale[i];
+        c_offset[i] = K.offset[i];
+        c_scale2[i] = K.scale2[i];
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int nfiles = A.nfiles;
     const int nstop = A.nstop < 1 ? 1 : A.nstop;
     const bool want_var = (A.typ_var == 0);
     const float* const* rows = reinterpret_cast<const float* const*>(tab->data);
     const float* const* vrows = reinterpret_cast<const float* const*>(tab->var);
+    auto data_row = [&](int e) -> const float* { return STRIDED ? RR.data0 + (size_t)e * RR.dstride : ld_row(rows, e); };
+    auto stat_row = [&](int e) -> const float* { return STRIDED ? RR.var0 + (size_t)e * RR.vstride : ld_row(vrows, e); };
 
     TransposeConsts tc;
     tc.init(lane);
@@ -59,7 +101,16 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
     unsigned tiles_done = 0, slow_count = 0;
 
     const long long ntiles = (A.nvox + 31) >> 5;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    long long clk[5] = {0, 0, 0, 0, 0};
+    auto grab_tile = [&]() -> long long {
+        long long t = 0;
+        if (lane == 0) t = (long long)atomicAdd(RR.next_tile, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    for (;;) {
+        const long long tile = grab_tile();
+        if (tile >= ntiles) break;
+        const long long tc0 = clock64();
         const long long v = (tile << 5) + lane;
         const bool act = v < A.nvox;
 
@@ -77,7 +128,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
 #pragma unroll
             for (int i = 0; i < H; i++) {
                 key[i] = CUDART_NAN_F;
-                if (act && e0 + i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(ld_row(rows, e0 + i) + v));
+                if (act && e0 + i < nfiles) asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(key[i]) : "l"(data_row(e0 + i) + v));
             }
             asm volatile("" ::: "memory");
             unsigned inv0 = 0u, inv1 = 0u;
@@ -88,7 +139,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
                 const bool ok = (d == d);
                 double w;
                 if constexpr (UNIT) w = (double)d;
-                else w = (__ldg(tab->offset + e0 + i) + (double)d) * __ldg(tab->scale + e0 + i);
+                else w = (c_offset[e0 + i] + (double)d) * c_scale[e0 + i];
                 if (i < 4 && r == 0) {         // pivot: first valid sample among the first four exposures
                     p = (ok && !have_p) ? w : p;
                     have_p = have_p || ok;
@@ -124,6 +175,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
         int n = 0;
 #pragma unroll
         for (int s = 0; s < R; s++) n += nr[s];
+        const long long tc1 = clock64();
 
         // ---- clip iterations on the R sorted columns ---------------------------------------------
         double mean = sum / (double)n;
@@ -146,25 +198,42 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
                 double var_k = __fma_rn(S2, rm, -(dm1 * dm1));
                 if (!(var_k >= 0x1p-13 * (S2_0 * rm))) { slow = true; break; }
                 sigma = sqrt(var_k);
-                // k-th smallest key of the R windows (k = m/2): bisection on the sortable bit pattern
-                const int k = m >> 1;
-                unsigned lo = 0x00800000u, hi = 0xFF7FFFFFu;   // sortable(-FLT_MAX) .. sortable(+FLT_MAX): every probe is finite
-                while (lo < hi) {
-                    const unsigned mid = lo + ((hi - lo) >> 1);
-                    const float x = key_unsortable(mid);
-                    int c = 0;
+                // Median of the R windows (tools.c:45-48) by elimination: to skip `need` keys, look at the key t = ceil(need / R)
+                // places into every window; the smallest of those has at most R (t - 1) < need keys below it, so it and the
+                // t - 1 keys before it in its window can all be skipped.  ~log(need) / log(R / (R - 1)) rounds of R loads.
+                int pos[R];
 #pragma unroll
-                    for (int s = 0; s < R; s++) c += min(max(count_col<H, true>(sk[s], lane, x), a[s]), b[s]) - a[s];
-                    if (c >= k + 1) hi = mid;
-                    else lo = mid + 1;
-                }
-                float kh = key_unsortable(lo), kl = kh;
-                if (!(m & 1)) {                                // predecessor: largest key below the k-th
-                    kl = -CUDART_INF_F;
+                for (int s = 0; s < R; s++) pos[s] = a[s];
+                int need = (m & 1) ? (m >> 1) : (m >> 1) - 1;              // ranks below the lower middle
+                while (need > 0) {
+                    const int t = (need + R - 1) / R;
+                    float best = CUDART_INF_F;
+                    int bs = 0;
 #pragma unroll
                     for (int s = 0; s < R; s++) {
-                        const int pos = min(max(count_col<H, false>(sk[s], lane, kh), a[s]), b[s]);
-                        if (pos > a[s]) kl = fmaxf(kl, sk[s][pos - 1][lane]);
+                        const int q = pos[s] + t - 1;
+                        const float x = q < b[s] ? sk[s][q][lane] : CUDART_INF_F;
+                        if (x < best) { best = x; bs = s; }
+                    }
+#pragma unroll
+                    for (int s = 0; s < R; s++) pos[s] += (s == bs) ? t : 0;
+                    need -= t;
+                }
+                float kl = CUDART_INF_F, kh;
+                int ls = 0;
+#pragma unroll
+                for (int s = 0; s < R; s++) {
+                    const float x = pos[s] < b[s] ? sk[s][pos[s]][lane] : CUDART_INF_F;
+                    if (x < kl) { kl = x; ls = s; }
+                }
+                kh = kl;
+                if (!(m & 1)) {                                                // upper middle: the next key
+                    kh = CUDART_INF_F;
+#pragma unroll
+                    for (int s = 0; s < R; s++) {
+                        const int q = pos[s] + (s == ls ? 1 : 0);
+                        const float x = q < b[s] ? sk[s][q][lane] : CUDART_INF_F;
+                        kh = fminf(kh, x);
                     }
                 }
                 kh = __uint_as_float(__float_as_uint(kh) & ~IDX);
@@ -202,8 +271,8 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
                     for (int q = a[s]; q < b[s]; q++) {
                         if (q == na[s]) { q = nb2[s]; if (q >= b[s]) break; }
                         const int i = (int)(__float_as_uint(sk[s][q][lane]) & IDX);
-                        const double dd = (double)__ldg(ld_row(rows, i) + v);
-                        const double w = UNIT ? dd : (__ldg(tab->offset + i) + dd) * __ldg(tab->scale + i);
+                        const double dd = (double)__ldg(data_row(i) + v);
+                        const double w = UNIT ? dd : (c_offset[i] + dd) * c_scale[i];
                         const double t = w - p;
                         T1 -= t;
                         S2 -= t * t;
@@ -218,6 +287,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
         int kept = 0;
 #pragma unroll
         for (int s = 0; s < R; s++) kept += b[s] - a[s];
+        const long long tc2 = clock64();
         if (slow) {
             const VoxelResultN<NB> r = exact_voxel_w<NB, UNIT>(rows, v, tab->scale, tab->offset, nfiles, A.nmax, A.nclip_low,
                                                                A.nclip_up, nstop);
@@ -228,6 +298,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
             slow_count++;
         }
         __syncwarp();
+        const long long tc3 = clock64();
 
         // ---- propagated variance over the kept set, one run of STAT rows at a time ----------------
         const ExpSet<NB> dropped = inval | rejected;
@@ -240,7 +311,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
                 float sv[H];
 #pragma unroll
                 for (int i = 0; i < H; i++)
-                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(ld_row(vrows, e0 + i < nfiles ? e0 + i : 0) + vs));
+                    asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(sv[i]) : "l"(stat_row(e0 + i < nfiles ? e0 + i : 0) + vs));
                 unsigned d0 = 0u, d1 = 0u;
 #pragma unroll
                 for (int s = 0; s < R; s++) {
@@ -249,7 +320,7 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
                 const unsigned long long bits = ((unsigned long long)d1 << 32) | d0;
 #pragma unroll
                 for (int i = 0; i < H; i++)
-                    if (!((bits >> i) & 1ull)) vsum += (double)sv[i] * __ldg(tab->scale2 + e0 + i);
+                    if (!((bits >> i) & 1ull)) vsum += UNIT ? (double)sv[i] : (double)sv[i] * c_scale2[e0 + i];
             }
         }
 
@@ -259,6 +330,8 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
             cnt_drop[k] += __popc(tc.apply(dropped.w[k]));
         }
         tiles_done++;
+        const long long tc4 = clock64();
+        clk[0] += tc1 - tc0; clk[1] += tc2 - tc1; clk[2] += tc3 - tc2; clk[3] += tc4 - tc3; clk[4]++;
 
         if (act) {
             double ov;
@@ -286,6 +359,10 @@ sigclip_runs_kernel(const ClipArgs A, const StackTable* __restrict__ tab, unsign
         }
     }
     if (slow_total != nullptr && slow_count) atomicAdd(slow_total, (unsigned long long)slow_count);
+    if (RR.phase_clk != nullptr && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) atomicAdd(reinterpret_cast<unsigned long long*>(RR.phase_clk) + k, (unsigned long long)clk[k]);
+    }
 }
 
 }  // namespace mb

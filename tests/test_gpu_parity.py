@@ -157,6 +157,25 @@ def test_mad_and_deep_stacks(n, vartype):
         assert_same_result(cuda().median_cuda(data), oracle.median_port(data), median=True)
 
 
+@pytest.mark.parametrize("n", [129, 192, 256, 257, 400, 500])
+def test_runs_kernel_deep_stacks(n):
+    """129 .. 512 exposures (sorted runs of 64, median by elimination over the runs, tiles handed out dynamically):
+    separate allocations (row table) and one [N][V] allocation (strided rows), ties, every variance mode."""
+    rng = np.random.default_rng(1000 + n)
+    shape = (2, 9, 31)     # 558 voxels: 18 tiles, the last one ragged
+    for ties in (False, True):
+        data, var = random_stack(rng, n, shape, nan_frac=0.1, outlier_frac=0.03, ties=ties)
+        for kw in (dict(nclip=3.0, vartype="propagate"),
+                   dict(scales=np.linspace(0.9, 1.1, n), offsets=np.linspace(-0.1, 0.1, n), nclip=(2.0, 2.5), vartype="stat_mean"),
+                   dict(scales=np.linspace(0.5, 2.0, n), nclip=1.5, nmax=4, vartype="propagate")):
+            want = oracle.combine_port(data, var, **kw)
+            for location in ("device_scattered", "device_stacked", "host"):
+                got = cuda().combine_cuda(data, var, location=location, **kw)
+                name = cuda().kernel_name()
+                assert "sigclip_runs<" in name and (("strided" in name) == (location != "device_scattered"))
+                assert_same_result(got, want)
+
+
 @pytest.mark.parametrize("location", ["device", "host"])
 def test_float64_exposures(location):
     rng = np.random.default_rng(8)
