@@ -208,8 +208,8 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream, bool* hi
         if (hist_fused != nullptr) *hist_fused = ctx.hist_fused && rc == MPDAF_B200_OK;
         return rc;
     }
-    // 129..512 float32 exposures, plain sigma clip: R sorted runs of 64 (sigclip_runs.cuh)
-    if (j.nfiles > 128 && j.nfiles <= kGenericMax && j.elem == MPDAF_B200_F32 && !j.median && !j.a.mad &&
+    // 129..512 float32 exposures, plain sigma clip or median: R sorted runs of 64 (sigclip_runs.cuh)
+    if (j.nfiles > 128 && j.nfiles <= kGenericMax && j.elem == MPDAF_B200_F32 && (j.median || !j.a.mad) &&
         std::getenv("MPDAF_B200_NO_RUNS") == nullptr) {
         char name[64] = "";
         LaunchCtx ctx;

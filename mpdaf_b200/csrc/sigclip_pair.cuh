@@ -838,7 +838,7 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
                         for (int j = 0; j < VB; j++) {
                             if (i0 + j < NB) {
                                 asm volatile("ld.global.cs.v2.f64 {%0, %1}, [%2];" : "=d"(sv[j].x), "=d"(sv[j].y) : "l"(vp));
-                                vp += S.vstride;
+                                if (i0 + j + 1 < A.nfiles) vp += S.vstride;       // slots beyond the stack re-read its last row (dropped anyway)
                             }
                         }
                         asm volatile("" ::: "memory");
@@ -854,10 +854,20 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             } else if (pair_ok) {
                 const float* vp = static_cast<const float*>(S.var0) + v0;
                 float2 sv[NB];
+                if (A.nfiles == NB) {
 #pragma unroll
-                for (int i = 0; i < NB; i++) {
-                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
-                    vp += S.vstride;
+                    for (int i = 0; i < NB; i++) {
+                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
+                        vp += S.vstride;
+                    }
+                } else {
+                    // fewer exposures than slots: the slots beyond the stack re-read its last row (their samples are
+                    // invalid -- NaN-filled by the tensor map -- hence dropped); a row beyond the stack is never addressed
+#pragma unroll
+                    for (int i = 0; i < NB; i++) {
+                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
+                        if (i + 1 < A.nfiles) vp += S.vstride;
+                    }
                 }
                 asm volatile("" ::: "memory");
                 count_tile();                     // the counter transposes run while the STAT rows are on their way

@@ -33,6 +33,24 @@ int mb_launch_runs(const mb::Job& j, bool unit, mb::LaunchCtx& ctx)
     rr.phase_clk = want_clk ? dbg_clk : nullptr;
     const bool strided = rr.dstride != 0 && (rr.var0 == nullptr || rr.vstride != 0) && std::getenv("MPDAF_B200_NO_STRIDED") == nullptr;
     if (strided) std::snprintf(ctx.name, ctx.name_len, "sigclip_runs<%dx64,%s,strided>", runs, unit ? "unit" : "scaled");
+    if (j.median) {
+        std::snprintf(ctx.name, ctx.name_len, "median_runs<%dx64%s>", runs, strided ? ",strided" : "");
+        auto launch_median = [&](auto kernel, int smem, int wpb) -> int {
+            MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const long long ntiles = (j.a.nvox + 31) / 32;
+            const int grid = (int)std::max(1LL, std::min((ntiles + wpb - 1) / wpb, (long long)ctx.sm_count));
+            if (ctx.slow_n == nullptr) return fail(MPDAF_B200_ERR_ARG, "runs kernel needs the device tile counter");
+            MB_CUDA(cudaMemsetAsync(ctx.slow_n, 0, sizeof(unsigned), ctx.stream));
+            kernel<<<grid, 32 * wpb, smem, ctx.stream>>>(j.a, (const StackTable*)j.table_dev, rr);
+            MB_CUDA(cudaGetLastError());
+            ctx.launches++;
+            return MPDAF_B200_OK;
+        };
+        if (runs == 4) return strided ? launch_median(median_runs_kernel<4, true>, RunsCfg<4>::smem, RunsCfg<4>::WPB)
+                                      : launch_median(median_runs_kernel<4, false>, RunsCfg<4>::smem, RunsCfg<4>::WPB);
+        return strided ? launch_median(median_runs_kernel<8, true>, RunsCfg<8>::smem, RunsCfg<8>::WPB)
+                       : launch_median(median_runs_kernel<8, false>, RunsCfg<8>::smem, RunsCfg<8>::WPB);
+    }
     auto launch = [&](auto kernel, int smem, const auto& consts, int wpb) -> int {
         MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const long long ntiles = (j.a.nvox + 31) / 32;

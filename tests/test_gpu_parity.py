@@ -174,6 +174,14 @@ def test_runs_kernel_deep_stacks(n):
                 name = cuda().kernel_name()
                 assert "sigclip_runs<" in name and (("strided" in name) == (location != "device_scattered"))
                 assert_same_result(got, want)
+        # the median of deep stacks runs on the same sorted runs (bit-identical to the reference)
+        data[1][0, 0, :5] = np.inf
+        data[2][0, 1, :5] = -np.inf
+        want = oracle.median_port(data)
+        for location in ("device", "host"):
+            got = cuda().median_cuda(data, location=location)
+            assert "median_runs<" in cuda().kernel_name()
+            assert_same_result(got, want, median=True)
 
 
 @pytest.mark.parametrize("location", ["device", "host"])
@@ -219,6 +227,46 @@ def test_float64_ties_and_non_finite_samples():
         got = cuda().combine_cuda(data, var, vartype=vartype, nclip=2.0, location="device_pitched")
         assert "f64" in cuda().kernel_name()
         assert_same_result(got, want)
+
+
+@pytest.mark.parametrize("dtype,n", [(np.float32, 5), (np.float32, 41), (np.float64, 8), (np.float64, 31)])
+def test_partial_bucket_reads_no_row_beyond_the_stack(dtype, n):
+    """A stack that does not fill its depth bucket, placed at the very END of its own device allocation: the STAT loads of
+    the pair kernel must not address the bucket's empty slots (an out-of-bounds read there is an illegal-address fault)."""
+    import torch
+    rng = np.random.default_rng(77 + n)
+    shape = (3, 16, 32)                      # 1536 voxels: rows are multiples of 128 bytes
+    nvox = int(np.prod(shape))
+    data, var = random_stack(rng, n, shape, nan_frac=0.1, outlier_frac=0.04, dtype=dtype)
+    want = oracle.combine_port(data, var, nclip=3.0)
+    dev = torch.device("cuda", 0)
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    seg = 64 << 20                            # blocks of this size come straight from cudaMalloc: nothing mapped behind them
+    bufs = []
+    ptrs = []
+    for arrs in (data, var):
+        buf = torch.empty(seg // np.dtype(dtype).itemsize, dtype=tdt, device=dev)
+        tail = buf[buf.numel() - n * nvox:].view(n, nvox)
+        tail.copy_(torch.from_numpy(np.stack([a.reshape(-1) for a in arrs])))
+        bufs.append(buf)
+        ptrs.append([tail[i].data_ptr() for i in range(n)])
+    out = torch.empty(nvox, dtype=torch.float64, device=dev)
+    outvar = torch.empty(nvox, dtype=torch.float64, device=dev)
+    expmap = torch.empty(nvox, dtype=torch.int32, device=dev)
+    sel = np.zeros(n, dtype=np.intc)
+    val = np.zeros(n, dtype=np.intc)
+    from mpdaf_b200.ctools import DEVICE, check, ctools
+    kd = (ctypes.c_void_p * n)(*ptrs[0])
+    kv = (ctypes.c_void_p * n)(*ptrs[1])
+    rc = ctools.mpdaf_b200_sigma_clipping_arrays(
+        n, ctypes.cast(kd, ctypes.POINTER(ctypes.c_void_p)), ctypes.cast(kv, ctypes.POINTER(ctypes.c_void_p)),
+        np.dtype(dtype).itemsize, nvox, DEVICE, 0, out.data_ptr(), outvar.data_ptr(), expmap.data_ptr(), None, None, sel, val,
+        2, 3.0, 3.0, 2, 0, 0, torch.cuda.current_stream(dev).cuda_stream)
+    check(rc, "combine")
+    torch.cuda.synchronize(dev)               # a fault would surface here
+    assert "sigclip_pair<" in cuda().kernel_name()
+    got = dict(data=out.cpu().numpy(), var=outvar.cpu().numpy(), expmap=expmap.cpu().numpy(), select_pix=sel, valid_pix=val)
+    assert_same_result(got, want)
 
 
 def test_edge_cases():

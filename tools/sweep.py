@@ -15,7 +15,8 @@ PLANE = 326 * 331
 DEPTHS = (4, 8, 12, 16, 24, 32, 48, 64, 96, 128, 256)
 MODES = (("median", ["--median"]), ("propagate", ["--var", "propagate"]), ("propagate+scales", ["--var", "propagate", "--scaled"]),
          ("stat_mean", ["--var", "stat_mean"]), ("stat_one+scales", ["--var", "stat_one", "--scaled"]),
-         ("mad+propagate", ["--var", "propagate", "--mad"]))
+         ("mad+propagate", ["--var", "propagate", "--mad"]),
+         ("f64 propagate+scales", ["--var", "propagate", "--scaled", "--f64"]))
 
 
 def main():
@@ -26,7 +27,9 @@ def main():
     quick = "--quick" in sys.argv
     for n in DEPTHS:
         for name, flags in MODES:
-            planes_per_voxel = n * (2 if "propagate" in name else 1)
+            if "f64" in name and n > 128:
+                continue
+            planes_per_voxel = n * (2 if "propagate" in name else 1) * (2 if "f64" in name else 1)
             # ~6 GB of samples per case and never fewer than 32 planes: 3.4 Mvoxel fill the 148 SMs many times over
             # (round 1 ran the deep rows on 2-7 planes: 0.15 ms kernels, not throughput measurements)
             nz = max(32, min(512, int(6e9 / (planes_per_voxel * 4 * PLANE))))
