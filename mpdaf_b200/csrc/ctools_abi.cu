@@ -229,8 +229,8 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream, bool* hi
         g_last_launches += ctx.launches;
         return rc;
     }
-    // float64 samples, sigma clip, up to 48 exposures on equally pitched rows: the pair kernel with float64 stages
-    if (j.elem == MPDAF_B200_F64 && !j.median && j.nfiles <= 48) {
+    // float64 samples, sigma clip, up to 64 exposures on equally pitched rows: the pair kernel with float64 stages
+    if (j.elem == MPDAF_B200_F64 && !j.median && j.nfiles <= 64) {
         char name[64] = "";
         LaunchCtx ctx;
         ctx.sm_count = g_dev[device].sm_count;
@@ -245,7 +245,8 @@ int enqueue_combine_only(const Job& j, int device, cudaStream_t stream, bool* hi
         ctx.hist = hist;
         bool taken = false;
         const int rc = j.nfiles <= 12 ? mb_launch_pair64_12(j, unit, ctx, taken)
-                     : j.nfiles <= 24 ? mb_launch_pair64_24(j, unit, ctx, taken) : mb_launch_pair64_48(j, unit, ctx, taken);
+                     : j.nfiles <= 24 ? mb_launch_pair64_24(j, unit, ctx, taken)
+                     : j.nfiles <= 48 ? mb_launch_pair64_48(j, unit, ctx, taken) : mb_launch_pair64_64(j, unit, ctx, taken);
         if (rc != MPDAF_B200_OK || taken) {
             g_last_kernel = name;
             g_last_launches += ctx.launches;

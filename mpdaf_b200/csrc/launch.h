@@ -59,9 +59,10 @@ int fail(int code, const std::string& msg);   // records the message (ctools_abi
     int mb_launch_median_warp_##NB(const mb::Job& j, mb::LaunchCtx& ctx);
 MB_FOR_EACH_DEPTH(MB_DECLARE_DEPTH)
 #undef MB_DECLARE_DEPTH
-// float64 samples: pair kernel in three depth buckets (pair64_<NB>.cu)
+// float64 samples: pair kernel in four depth buckets (pair64_<NB>.cu)
 int mb_launch_pair64_12(const mb::Job& j, bool unit, mb::LaunchCtx& ctx, bool& taken);
 int mb_launch_pair64_24(const mb::Job& j, bool unit, mb::LaunchCtx& ctx, bool& taken);
 int mb_launch_pair64_48(const mb::Job& j, bool unit, mb::LaunchCtx& ctx, bool& taken);
+int mb_launch_pair64_64(const mb::Job& j, bool unit, mb::LaunchCtx& ctx, bool& taken);
 // multi-run kernel for 129..512 exposures (sigclip_runs.cuh); the stack table must already be on the device
 int mb_launch_runs(const mb::Job& j, bool unit, mb::LaunchCtx& ctx);

@@ -98,7 +98,8 @@ struct PairSmem {
     unsigned hist[NB + 1];                                // voxels of this block by number of exposures kept
     unsigned pad[64];                                     // the clip loop may read up to five rows beyond the last column
 };
-static_assert(sizeof(PairSmem<48, float>) <= 227 * 1024 && sizeof(PairSmem<64, float>) <= 227 * 1024 && sizeof(PairSmem<48, double>) <= 227 * 1024, "shared memory");
+static_assert(sizeof(PairSmem<48, float>) <= 227 * 1024 && sizeof(PairSmem<64, float>) <= 227 * 1024 && sizeof(PairSmem<48, double>) <= 227 * 1024 &&
+                  sizeof(PairSmem<64, double>) <= 227 * 1024, "shared memory");
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {

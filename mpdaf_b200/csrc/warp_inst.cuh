@@ -80,7 +80,7 @@ inline bool encode_stack_map(TensorMap2D& out, const void* base, unsigned long l
     return true;
 }
 
-// Pair-packed TMA-pipelined sigma clip (sigclip_pair.cuh): float32 stacks up to 64 deep (float64: up to 48) whose rows
+// Pair-packed TMA-pipelined sigma clip (sigclip_pair.cuh): float32 / float64 stacks up to 64 deep whose rows
 // are equally pitched and 16-byte aligned.  Returns MPDAF_B200_OK and sets `taken` when the stack qualifies.
 template <int NB, typename ET = float>
 int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
@@ -88,7 +88,7 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
     taken = false;
     constexpr long long ES = (long long)sizeof(ET);
     constexpr bool F64 = sizeof(ET) == 8;
-    if constexpr (NB > 64 || (F64 && NB > 48)) {
+    if constexpr (NB > 64) {
         return MPDAF_B200_OK;
     } else {
         const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr;   // read per call: tests switch kernel families

@@ -194,9 +194,9 @@ def test_float64_exposures(location):
     assert_same_result(cuda().median_cuda(data, location=location), oracle.median_port(data), median=True)
 
 
-@pytest.mark.parametrize("n", [2, 5, 12, 13, 24, 37, 48])
+@pytest.mark.parametrize("n", [2, 5, 12, 13, 24, 37, 48, 49, 64])
 def test_float64_exposures_on_the_pair_kernel(n):
-    """BITPIX -64 stacks up to 48 deep on equally pitched rows: the pair kernel with float64 stages (float64 samples in
+    """BITPIX -64 stacks up to 64 deep on equally pitched rows: the pair kernel with float64 stages (float64 samples in
     the moments and in every exact decision, float64 STAT products); every mode, host route included."""
     rng = np.random.default_rng(300 + n)
     data, var = random_stack(rng, n, (5, 9, 11), nan_frac=0.1, outlier_frac=0.04, dtype=np.float64)
