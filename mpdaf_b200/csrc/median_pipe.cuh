@@ -5,11 +5,11 @@
 // valid counters) and src/tools.c:39-51 (median of the sorted samples, mean of the two middle ones for even n).
 //
 // The round-1 kernel (median_warp_kernel, sigclip_warp.cuh) gathers the exposure rows into registers itself and is
-// bound by the latency of those loads (0.68 of the measured HBM peak at N = 12).  Here a producer warp streams
-// [NB][64] tiles into a deep ring of shared-memory stages with cp.async.bulk.tensor (TMA, mbarrier completion) and
-// the consumer warps only ever read shared memory: a lane takes TWO neighbouring voxels of a tile (two independent
-// register sorting networks: twice the instruction-level parallelism, 16-byte output stores), hands the stage back
-// as soon as the samples are in registers, and the kernel runs at the rate the ring can be refilled.
+// bound by the latency of those loads (0.68 of the measured HBM peak at N = 12).  Here every warp keeps up to four
+// shared-memory stages of its own filled with [NB][64] tiles by cp.async.bulk.tensor (TMA, mbarrier completion) and
+// only ever reads shared memory: a lane takes TWO neighbouring voxels of a tile (two independent register sorting
+// networks: twice the instruction-level parallelism, 16-byte output stores), requests the stage's next tile as soon
+// as the samples are in registers, and the kernel runs at the rate the stages can be refilled.
 // Invalid samples are replaced alternately by +inf / -inf, so that the valid ones stay centred in the sorted stack
 // and the median sits in two fixed registers; results are bit-identical to the reference.
 #pragma once
@@ -18,6 +18,135 @@
 
 namespace mb {
 
+template <int NB>
+struct MedianOwnCfg {
+    // shallow stacks take wider tiles (fewer, larger TMA copies), processed by the warp as SUB sub-tiles of 64 voxels
+    static constexpr int SUB = NB <= 16 ? 2 : 1;   // (256-voxel boxes faulted on the B200: not pursued)
+    static constexpr int TV = 64 * SUB;                                          // voxels per tile
+    static constexpr int stage_bytes = NB * TV * 4;
+    // Every warp is a consumer that owns SPW stages and refills them itself (no producer warp, as in sigclip_pair.cuh):
+    // its j-th tile uses its stage j % SPW, whose next tile (j + SPW) is requested the moment the samples are in registers.
+    static constexpr int c_regs = 2048 / (2 * NB + 40);                         // two voxels of NB samples per lane
+    static constexpr int C = c_regs < 16 ? (c_regs < 2 ? 2 : c_regs) : 16;       // four warps per scheduler at most
+    static constexpr int st_fit = (200 * 1024) / stage_bytes;
+    static constexpr int SPW = st_fit / C > 4 ? 4 : st_fit / C;
+    static constexpr int ST = SPW * C;
+    static constexpr int threads = C * 32;
+    static_assert(SPW >= 1, "stack too deep for the pipelined median kernel");
+};
+
+template <int NB>
+struct MedianOwnSmem {
+    float stage[MedianOwnCfg<NB>::ST][NB][MedianOwnCfg<NB>::TV];
+    unsigned long long full[MedianOwnCfg<NB>::ST];
+};
+
+template <int NB>
+__global__ void __launch_bounds__(MedianOwnCfg<NB>::threads, 1)
+median_own_kernel(const ClipArgs A, const long long ntiles, const __grid_constant__ TmaMaps M)
+{
+    using Cfg = MedianOwnCfg<NB>;
+    constexpr int C = Cfg::C, ST = Cfg::ST, SPW = Cfg::SPW;
+    constexpr int W = ExpSet<NB>::W;
+    constexpr int SUB = Cfg::SUB, TV = Cfg::TV;
+    constexpr unsigned kTileBytes = NB * TV * sizeof(float);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    MedianOwnSmem<NB>& sm = *reinterpret_cast<MedianOwnSmem<NB>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < ST; s++) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int c = warp;
+    const unsigned one = (unsigned)(A.nfiles > 0);     // opaque 1 / -1 for the IMAD form of the compare-exchange
+    const unsigned minus_one = 0u - one;
+    TransposeConsts tc;
+    tc.init(lane);
+    unsigned cnt[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) cnt[k] = 0u;
+    unsigned tiles_done = 0;
+    // this warp's j-th tile is the block's tile j * C + c, i.e. tile blockIdx.x + (j * C + c) * gridDim.x of the slab
+    auto request_tile = [&](long long j) {             // lane 0 only
+        const long long t = (long long)blockIdx.x + (j * C + c) * (long long)gridDim.x;
+        if (t >= ntiles) return;
+        const unsigned st = (unsigned)(c * SPW + (int)(j % SPW));
+        mbar_expect_tx(&sm.full[st], kTileBytes);
+        tma_load_2d(&sm.stage[st][0][0], &M.data, (int)(t * TV), 0, &sm.full[st]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < SPW; j++) request_tile(j);
+    }
+    long long tile = (long long)blockIdx.x + (long long)c * gridDim.x;
+    for (long long j = 0; tile < ntiles; j++, tile += (long long)C * gridDim.x) {
+        const unsigned st = (unsigned)(c * SPW + (int)(j % SPW)), ph = (unsigned)(j / SPW) & 1u;
+        const float (*dt)[TV] = sm.stage[st];
+        mbar_wait(&sm.full[st], ph);
+#pragma unroll
+        for (int sub = 0; sub < SUB; sub++) {
+            const long long v0 = tile * TV + 64 * sub + 2 * lane;
+            float key[2][NB];
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                const float2 dd = *reinterpret_cast<const float2*>(&dt[i][64 * sub + 2 * lane]);
+                key[0][i] = dd.x;
+                key[1][i] = dd.y;
+            }
+            if (sub == SUB - 1) {
+                __syncwarp();
+                if (lane == 0) request_tile(j + SPW);          // the samples are in registers: the stage is refilled at once
+            }
+            double med[2];
+            int n[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                ExpSet<NB> inval;
+                bool flip = false;                         // parity of the invalid samples seen so far
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    const float d = key[h][i];
+                    const bool ok = (d == d);              // rows beyond nfiles and voxels beyond nvox arrive as NaN (TMA fill)
+                    key[h][i] = ok ? d : (flip ? -CUDART_INF_F : CUDART_INF_F);
+                    if (!ok) {
+                        flip = !flip;
+                        inval.set(i);
+                    }
+                }
+                n[h] = NB - inval.count();
+                sort_keys_mixed<NB, 1>(key[h], one, minus_one);
+                // the first invalid sample went to +inf: the valid ones occupy slots [floor((NB - n) / 2), ...) and their
+                // middle is slot NB/2 - 1 (odd n) or slots NB/2 - 1 and NB/2 (even n)
+                const double lo = (double)key[h][NB / 2 - 1], hi = (double)key[h][NB / 2];
+                med[h] = (n[h] & 1) ? lo : (lo + hi) * 0.5;                         // tools.c:45-48
+                if (n[h] == 0) med[h] = CUDART_NAN;                                 // merging.c:239
+#pragma unroll
+                for (int kk = 0; kk < W; kk++) cnt[kk] += __popc(tc.apply(inval.w[kk]));
+            }
+            if (v0 + 1 < A.nvox) {
+                *reinterpret_cast<double2*>(A.out + v0) = make_double2(med[0], med[1]);
+                *reinterpret_cast<int2*>(A.expmap + v0) = make_int2(n[0], n[1]);
+            } else if (v0 < A.nvox) {
+                A.out[v0] = med[0];
+                A.expmap[v0] = n[0];
+            }
+        }
+        tiles_done++;
+    }
+    const unsigned seen = tiles_done * (unsigned)TV;
+#pragma unroll
+    for (int kk = 0; kk < W; kk++) {
+        const int e = 32 * kk + lane;
+        if (e < A.nfiles) atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt[kk]));
+    }
+}
+
+// ---- the producer / consumer form (first round-2 version): one producer lane keeps a ring of ST stages full, fifteen
+// consumer warps.  Still the faster one at N <= 12 on a full-size cube (cfg2: 5707 GB/s against 5090 for the form
+// above, which wins by 9 .. 10 % from N = 16 on); the launcher chooses (warp_inst.cuh).
 template <int NB>
 struct MedianPipeCfg {
     // shallow stacks take wider tiles (one lane issues the TMA copies: about one per 270 cycles), processed by the

@@ -240,13 +240,26 @@ int launch_median_warp_impl(const Job& j, LaunchCtx& ctx)
         if (dp != 0 && j.a.nvox >= 1 && j.a.nvox < 0x7FFFFF00LL && !(reinterpret_cast<uintptr_t>(j.a.out) & 15u) &&
             !(reinterpret_cast<uintptr_t>(j.a.expmap) & 7u) &&
             encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * dp, (unsigned)MedianPipeCfg<NB>::TV, NB, true)) {
-            using Cfg = MedianPipeCfg<NB>;
-            std::snprintf(ctx.name, ctx.name_len, "median_pipe<%d>", NB);
-            const int smem = (int)sizeof(MedianPipeSmem<NB>);
-            MB_CUDA(cudaFuncSetAttribute(median_pipe_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            const long long ntiles = (j.a.nvox + Cfg::TV - 1) / Cfg::TV;
+            // two forms of the pipeline (median_pipe.cuh; both tile widths are the same): a producer lane + 15 consumer
+            // warps up to 12 exposures, warps that own and refill their stages from 16 on; MPDAF_B200_MEDIAN_PIPE=1|2 forces one
+            const char* force = std::getenv("MPDAF_B200_MEDIAN_PIPE");
+            const bool own = force ? std::atoi(force) == 2 : NB > 12;
+            static_assert(MedianPipeCfg<NB>::TV == MedianOwnCfg<NB>::TV, "tile width");
+            const long long ntiles = (j.a.nvox + MedianPipeCfg<NB>::TV - 1) / MedianPipeCfg<NB>::TV;
             const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
-            median_pipe_kernel<NB><<<grid, Cfg::threads, smem, ctx.stream>>>(j.a, ntiles, maps);
+            if (own) {
+                using Cfg = MedianOwnCfg<NB>;
+                std::snprintf(ctx.name, ctx.name_len, "median_pipe<%d,own>", NB);
+                const int smem = (int)sizeof(MedianOwnSmem<NB>);
+                MB_CUDA(cudaFuncSetAttribute(median_own_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                median_own_kernel<NB><<<grid, Cfg::threads, smem, ctx.stream>>>(j.a, ntiles, maps);
+            } else {
+                using Cfg = MedianPipeCfg<NB>;
+                std::snprintf(ctx.name, ctx.name_len, "median_pipe<%d>", NB);
+                const int smem = (int)sizeof(MedianPipeSmem<NB>);
+                MB_CUDA(cudaFuncSetAttribute(median_pipe_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                median_pipe_kernel<NB><<<grid, Cfg::threads, smem, ctx.stream>>>(j.a, ntiles, maps);
+            }
             MB_CUDA(cudaGetLastError());
             ctx.launches++;
             return MPDAF_B200_OK;
