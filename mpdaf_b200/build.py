@@ -17,7 +17,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "_ctools.so")
 DEPTHS = (4, 8, 12, 16, 24, 32, 48, 64, 96, 128)
 SOURCES = ("ctools_abi.cu", "fits_reader.cpp", "host_tools.cpp") + tuple(f"warp_{n}.cu" for n in DEPTHS) + ("warp_runs.cu", "pair64_12.cu", "pair64_24.cu", "pair64_48.cu", "pair64_64.cu")
-HEADERS = ("combine_kernels.cuh", "stack_common.cuh", "sigclip_warp.cuh", "sigclip_pair.cuh", "median_pipe.cuh", "sigclip_runs.cuh", "warp_inst.cuh", "launch.h",
+HEADERS = ("combine_kernels.cuh", "stack_common.cuh", "sigclip_warp.cuh", "sigclip_pair.cuh", "sigclip_duo.cuh", "median_pipe.cuh", "sigclip_runs.cuh", "warp_inst.cuh", "launch.h",
            "sort_networks.cuh", "synth_core.h", "fits_reader.h", os.path.join("..", "..", "include", "mpdaf_b200.h"))
 
 NVCC_FLAGS = [

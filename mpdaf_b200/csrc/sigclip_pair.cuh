@@ -179,9 +179,11 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
                                                                 const unsigned* __restrict__ count, unsigned cap,
                                                                 unsigned long long* slow_total)
 {
-    __shared__ double s_w[4][64];            // valid samples in file order (later: the kept samples' variances)
-    __shared__ double s_s[4][64];            // ascending
-    __shared__ unsigned char s_f[4][64];     // exposure of the ascending samples
+    constexpr int NS = (NB + 31) / 32;       // samples per lane (up to 128 exposures: the duo kernel's queue comes here too)
+    constexpr int NSLOT = NS * 32;
+    __shared__ double s_w[4][NSLOT];         // valid samples in file order (later: the kept samples' variances)
+    __shared__ double s_s[4][NSLOT];         // ascending
+    __shared__ unsigned char s_f[4][NSLOT];  // exposure of the ascending samples
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const ET* data0 = static_cast<const ET*>(S.data0);
     const ET* var0 = static_cast<const ET*>(S.var0);
@@ -195,22 +197,30 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
     unsigned char* sf = s_f[wp];
     for (unsigned q = blockIdx.x * 4 + wp; q < nq; q += gridDim.x * 4) {
         const long long v = (long long)queue[q];
-        double w[2];
-        bool ok[2];
+        double w[NS];
+        bool ok[NS];
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < NS; s++) {
             const int i = lane + 32 * s;
             const ET x = i < nfiles ? __ldg(data0 + (size_t)i * S.dstride + v) : (ET)CUDART_NAN;
             ok[s] = (x == x);
             const double2 os = S.os[i < NB ? i : 0];
             w[s] = UNIT ? (double)x : (os.x + (double)x) * os.y;                 // merging.c:426
         }
-        const unsigned b0 = __ballot_sync(0xffffffffu, ok[0]), b1 = __ballot_sync(0xffffffffu, ok[1]);
-        const int n0 = __popc(b0), n = n0 + __popc(b1);
-        const int pos[2] = {__popc(b0 & lt), n0 + __popc(b1 & lt)};
+        unsigned bal[NS];
+        int pos[NS];
+        int n = 0, first_valid = 0;
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            bal[s] = __ballot_sync(0xffffffffu, ok[s]);
+            pos[s] = n + __popc(bal[s] & lt);
+            if (n == 0 && bal[s]) first_valid = 32 * s + __ffs(bal[s]) - 1;
+            n += __popc(bal[s]);
+        }
         __syncwarp();
-        if (ok[0]) fw[pos[0]] = w[0];
-        if (ok[1]) fw[pos[1]] = w[1];
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+            if (ok[s]) fw[pos[s]] = w[s];
         __syncwarp();
         double mean = CUDART_NAN, sigma = 0.0;
         int a = 0, b = n;
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
         if (n >= 2) {
             // ascending copy by ranking (equal values keep their file order: any order of equal values gives the same sums)
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
+            for (int s = 0; s < NS; s++) {
                 if (!ok[s]) continue;
                 int r = 0;
                 for (int j = 0; j < n; j++) {
@@ -261,7 +271,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
                 const double cup = med + (A.nclip_up * sigma);
                 int ni = 0, nle = 0;
 #pragma unroll
-                for (int s = 0; s < 2; s++) {
+                for (int s = 0; s < NS; s++) {
                     const int j = a + lane + 32 * s;
                     const double x = j < b ? sw[j] : 0.0;
                     const bool gt = (j < b) && (x > clo), in = gt && (x < cup);      // strict window, tools.c:95
@@ -288,10 +298,10 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
                 // variances of the kept samples in the order of their values (merging.c:461-462)
                 __syncwarp();
 #pragma unroll
-                for (int s = 0; s < 2; s++) {
+                for (int s = 0; s < NS; s++) {
                     const int j = a + lane + 32 * s;
                     if (j < b) {
-                        const int i = n >= 2 ? (int)sf[j] : (b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1);
+                        const int i = n >= 2 ? (int)sf[j] : first_valid;
                         fw[j - a] = (double)__ldg(var0 + (size_t)i * S.vstride + v) * S.scale2[i];
                     }
                 }
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(128) sigclip_pair_slow_kernel(const PairArgs<N
         }
         if (n >= 2) {
 #pragma unroll
-            for (int s = 0; s < 2; s++) {
+            for (int s = 0; s < NS; s++) {
                 const int j = lane + 32 * s;
                 if (j < n && (j < a || j >= b)) atomicAdd(A.select_cnt + sf[j], ~0ull);   // -1: valid but rejected
             }

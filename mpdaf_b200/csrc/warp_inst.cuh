@@ -12,6 +12,7 @@
 #include "launch.h"
 #include "sigclip_warp.cuh"
 #include "sigclip_pair.cuh"
+#include "sigclip_duo.cuh"
 #include "median_pipe.cuh"
 
 namespace mb {
@@ -165,13 +166,89 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
     }
 }
 
+// Pair kernel with the stack split between two lanes (sigclip_duo.cuh): float32 stacks of 65 .. 128 exposures on equally
+// pitched, 16-byte aligned rows, no MAD.
+template <int NB>
+int launch_duo_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
+{
+    taken = false;
+    if constexpr (NB != 96 && NB != 128) {
+        return MPDAF_B200_OK;
+    } else {
+        constexpr int HB = NB / 2;
+        const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr || std::getenv("MPDAF_B200_NO_DUO") != nullptr;
+        const bool need_var = j.a.typ_var == 0;
+        if (off || j.median || j.a.mad || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL || j.nfiles <= HB) return MPDAF_B200_OK;
+        auto pitch_of = [&](const void* const* rows) -> unsigned long long {
+            if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
+            const long long step = static_cast<const char*>(rows[1]) - static_cast<const char*>(rows[0]);
+            if (step < j.a.nvox * 4 || (step & 15) != 0) return 0ull;
+            for (int i = 2; i < j.nfiles; i++)
+                if (static_cast<const char*>(rows[i]) - static_cast<const char*>(rows[i - 1]) != step) return 0ull;
+            return (unsigned long long)(step >> 2);
+        };
+        const unsigned long long dp = pitch_of(j.data), vp = need_var ? pitch_of(j.var) : 0ull;
+        if (dp == 0 || (need_var && vp == 0)) return MPDAF_B200_OK;
+        if ((reinterpret_cast<uintptr_t>(j.a.out) & 15u) || (reinterpret_cast<uintptr_t>(j.a.outvar) & 15u) || (reinterpret_cast<uintptr_t>(j.a.expmap) & 7u))
+            return MPDAF_B200_OK;
+        TmaMaps maps;
+        std::memset(&maps, 0, sizeof(maps));
+        if (!encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * dp, 32u, NB, true)) return MPDAF_B200_OK;
+        if (need_var && !encode_stack_map(maps.stat, j.var[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * vp, 32u, NB, false)) return MPDAF_B200_OK;
+        static PairArgs<NB> s;     // (12 KB: kept off the stack; launches are serialized by the library's call mutex)
+        std::memset(&s, 0, sizeof(s));
+        s.data0 = j.data[0];
+        s.var0 = need_var ? j.var[0] : nullptr;
+        s.dstride = dp;
+        s.vstride = vp;
+        double osmax = 0.0;
+        for (int i = 0; i < NB; i++) {
+            const bool in = i < j.nfiles;
+            const double sc = (in && j.scale) ? j.scale[i] : 1.0, of = (in && j.offset) ? j.offset[i] : 0.0;
+            s.os[i] = make_double2(of, sc);
+            s.osp[i] = of * sc;
+            s.kscale[i] = (float)sc;
+            s.koffset[i] = (float)(of * sc);
+            s.scale2[i] = sc * sc;
+            s.scale2f[i] = (float)(sc * sc);
+            osmax = std::max(osmax, std::fabs(of * sc));
+        }
+        s.osmax = osmax;
+        s.hist = ctx.hist;
+        ctx.hist_fused = ctx.hist != nullptr;
+        using Cfg = DuoCfg<HB>;
+        std::snprintf(ctx.name, ctx.name_len, "sigclip_duo<%d,%s>", NB, unit ? "unit" : "scaled");
+        const long long ntiles = (j.a.nvox + 31) / 32;
+        auto launch = [&](auto kernel, auto slow_kernel) -> int {
+            const int smem = (int)sizeof(DuoSmem<HB>);
+            MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_CUDA(cudaMemsetAsync(ctx.slow_n, 0, sizeof(unsigned), ctx.stream));
+            const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
+            static const int pair_flags = std::getenv("MPDAF_B200_PAIR_FLAGS") ? std::atoi(std::getenv("MPDAF_B200_PAIR_FLAGS")) : (2 | 256);
+            kernel<<<grid, Cfg::threads, smem, ctx.stream>>>(s, j.a, ntiles, ctx.slow_q, ctx.slow_n, ctx.slow_cap, pair_flags, maps);
+            MB_CUDA(cudaGetLastError());
+            slow_kernel<<<ctx.sm_count * 8, 128, 0, ctx.stream>>>(s, j.a, ctx.slow_q, ctx.slow_n, ctx.slow_cap, ctx.slow);
+            MB_CUDA(cudaGetLastError());
+            ctx.launches += 2;
+            return MPDAF_B200_OK;
+        };
+        taken = true;
+        if (unit) return need_var ? launch(sigclip_duo_kernel<HB, true, true>, sigclip_pair_slow_kernel<NB, true>)
+                                  : launch(sigclip_duo_kernel<HB, true, false>, sigclip_pair_slow_kernel<NB, true>);
+        return need_var ? launch(sigclip_duo_kernel<HB, false, true>, sigclip_pair_slow_kernel<NB, false>)
+                        : launch(sigclip_duo_kernel<HB, false, false>, sigclip_pair_slow_kernel<NB, false>);
+    }
+}
+
 // Warp-tiled sigma clip (sigclip_warp.cuh): the main kernel for float32 stacks up to 128 deep.
 template <int NB>
 int launch_warp_impl(const Job& j, bool unit, LaunchCtx& ctx)
 {
     {
         bool taken = false;
-        const int rc = launch_pair_impl<NB>(j, unit, ctx, taken);
+        int rc = launch_pair_impl<NB>(j, unit, ctx, taken);
+        if (rc != MPDAF_B200_OK || taken) return rc;
+        rc = launch_duo_impl<NB>(j, unit, ctx, taken);
         if (rc != MPDAF_B200_OK || taken) return rc;
     }
     TileArgs<NB> s;

@@ -23,7 +23,7 @@ def cuda():
 def is_main_kernel(name):
     """The two sigma-clip kernel families for float32 stacks up to 128 deep: the pair-packed TMA-pipelined kernel
     (sigclip_pair.cuh: equally pitched, 16-byte aligned rows, <= 64 exposures, no MAD) and the warp-tiled one."""
-    return "sigclip_pair<" in name or "sigclip_warp<" in name
+    return "sigclip_pair<" in name or "sigclip_warp<" in name or "sigclip_duo<" in name
 
 
 @pytest.fixture(params=["pair", "warp"])
@@ -50,8 +50,10 @@ def test_register_kernels_every_bucket(n, location, family):
             got = cuda().combine_cuda(data, var, vartype=vartype, nclip=nclip, location=location, **kw)
             assert_same_result(got, want)
             assert is_main_kernel(cuda().kernel_name())
-            if family == "warp" or n > 64:
+            if family == "warp":
                 assert "sigclip_warp<" in cuda().kernel_name()
+            elif n > 64:
+                assert "sigclip_warp<" in cuda().kernel_name() or "sigclip_duo<" in cuda().kernel_name()
     want = oracle.median_port(data)
     got = cuda().median_cuda(data, location=location)
     assert_same_result(got, want, median=True)
@@ -155,6 +157,34 @@ def test_mad_and_deep_stacks(n, vartype):
             assert is_main_kernel(cuda().kernel_name()) and ("mad" in cuda().kernel_name()) == mad
     if n > 64:
         assert_same_result(cuda().median_cuda(data), oracle.median_port(data), median=True)
+
+
+@pytest.mark.parametrize("n", [65, 77, 96, 97, 111, 128])
+def test_duo_kernel_65_to_128_exposures(n):
+    """65 .. 128 exposures on pitched rows: the pair kernel with the stack split between two lanes (sigclip_duo.cuh):
+    every variance mode, scales, ties, heavy clipping, no clip at all, ragged last tile, host route."""
+    rng = np.random.default_rng(2000 + n)
+    shape = (3, 7, 23)      # 483 voxels: the last tile of 32 is ragged
+    for ties in (False, True):
+        data, var = random_stack(rng, n, shape, nan_frac=0.12, outlier_frac=0.04, ties=ties)
+        scales = np.linspace(0.9, 1.1, n)
+        offsets = np.linspace(-0.1, 0.1, n)
+        for kw in (dict(nclip=3.0, vartype="propagate"),
+                   dict(scales=scales, offsets=offsets, nclip=(2.0, 3.0), vartype="stat_mean"),
+                   dict(scales=scales, offsets=offsets, nclip=5.0, vartype="stat_one"),
+                   dict(scales=scales, offsets=offsets, nclip=1.5, nmax=5, vartype="propagate"),
+                   dict(nclip=5.0, nmax=0, vartype="stat_mean"),
+                   dict(nclip=1.0, nmax=3, nstop=40, vartype="propagate")):
+            want = oracle.combine_port(data, var, **kw)
+            for location in ("device_pitched", "host"):
+                got = cuda().combine_cuda(data, var, location=location, **kw)
+                assert "sigclip_duo<" in cuda().kernel_name(), cuda().kernel_name()
+                assert_same_result(got, want)
+    # non-finite samples and a tiny queue (voxels recomputed in place)
+    data[3][0, 0, :6] = np.inf
+    data[70 % n][0, 1, :6] = -np.inf
+    want = oracle.combine_port(data, var, nclip=2.0)
+    assert_same_result(cuda().combine_cuda(data, var, nclip=2.0, location="device_pitched"), want)
 
 
 @pytest.mark.parametrize("n", [129, 192, 256, 257, 400, 500])
@@ -687,7 +717,7 @@ def test_muse_planes_against_the_reference(cfg, tmp_path):
         got = cuda().combine_cuda(data, var, location=location, **kw)
         assert_same_result(got, want)
     name = cuda().kernel_name()
-    assert ("sigclip_pair<48" in name) if cfg == "cfg3" else ("sigclip_warp<96" in name)
+    assert ("sigclip_pair<48" in name) if cfg == "cfg3" else ("sigclip_duo<96" in name)
 
 
 # ---------------------------------------------------------------------------------------
