@@ -317,43 +317,34 @@ sigclip_duo_kernel(const PairArgs<2 * HB> S, const ClipArgs A, const long long n
                 const float yl = clo + Tb + e0m, xu = cup - Tb - e0m;
                 const float kL2 = yl * (yl >= 0.f ? c2f : c1f);
                 const float kU2 = xu * (xu >= 0.f ? c1f : c2f);
-                // the five keys next to either end of the window: two-way merge of the columns' ends
-                {
-                    int ia = ao, ib = ap;
-                    bool ok = true;
+                // Candidates: the keys at or below kL2 / at or above kU2.  Each column is sorted, so they are a prefix / suffix of
+                // EACH column's window: five independent probes per column and end (no merge of the two columns is needed;
+                // the boundary key of the union is the larger / smaller of the columns' last candidates).
+                unsigned BLo = 0xFF80u, BLp = 0xFF80u, BUo = 0x7F80u, BUp = 0x7F80u;
 #pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        const unsigned ua = ia < bo ? (unsigned)cA[ia * 64] : 0x7F80u;
-                        const unsigned ub = ib < bp ? (unsigned)cB[ib * 64] : 0x7F80u;
-                        const bool none = !(ia < bo) && !(ib < bp);
-                        const bool takeA = (ia < bo) && (!(ib < bp) || fkey(ua) <= fkey(ub));
-                        const unsigned u = takeA ? ua : ub;
-                        ok = ok && !none && !(fkey(u) > kL2);
-                        if (ok) {
-                            if (takeA) jl_o++; else jl_p++;
-                            BL = u;
-                        }
-                        if (takeA) ia++; else ib++;
-                    }
+                for (int j = 0; j < 5; j++) {
+                    const bool ia = ao + j < bo, ib = ap + j < bp;
+                    const unsigned ua = ia ? (unsigned)cA[(ao + j) * 64] : 0x7F80u;
+                    const unsigned ub = ib ? (unsigned)cB[(ap + j) * 64] : 0x7F80u;
+                    const bool ca = ia && !(fkey(ua) > kL2), cb = ib && !(fkey(ub) > kL2);
+                    jl_o += ca ? 1 : 0;
+                    jl_p += cb ? 1 : 0;
+                    BLo = ca ? ua : BLo;
+                    BLp = cb ? ub : BLp;
                 }
-                {
-                    int ia = bo - 1, ib = bp - 1;
-                    bool ok = true;
 #pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        const unsigned ua = ia >= ao ? (unsigned)cA[ia * 64] : 0xFF80u;
-                        const unsigned ub = ib >= ap ? (unsigned)cB[ib * 64] : 0xFF80u;
-                        const bool none = !(ia >= ao) && !(ib >= ap);
-                        const bool takeA = (ia >= ao) && (!(ib >= ap) || fkey(ua) >= fkey(ub));
-                        const unsigned u = takeA ? ua : ub;
-                        ok = ok && !none && !(fkey(u) < kU2);
-                        if (ok) {
-                            if (takeA) ju_o++; else ju_p++;
-                            BU = u;
-                        }
-                        if (takeA) ia--; else ib--;
-                    }
+                for (int j = 0; j < 5; j++) {
+                    const bool ia = bo - 1 - j >= ao, ib = bp - 1 - j >= ap;
+                    const unsigned ua = ia ? (unsigned)cA[(bo - 1 - j) * 64] : 0xFF80u;
+                    const unsigned ub = ib ? (unsigned)cB[(bp - 1 - j) * 64] : 0xFF80u;
+                    const bool ca = ia && !(fkey(ua) < kU2), cb = ib && !(fkey(ub) < kU2);
+                    ju_o += ca ? 1 : 0;
+                    ju_p += cb ? 1 : 0;
+                    BUo = ca ? ua : BUo;
+                    BUp = cb ? ub : BUp;
                 }
+                BL = jl_o == 0 ? BLp : (jl_p == 0 ? BLo : (fkey(BLo) >= fkey(BLp) ? BLo : BLp));
+                BU = ju_o == 0 ? BUp : (ju_p == 0 ? BUo : (fkey(BUo) <= fkey(BUp) ? BUo : BUp));
                 const int jl = jl_o + jl_p, ju = ju_o + ju_p;
                 const bool many = jl > 4 || ju > 4 || jl + ju > m;
                 go_slow = bad || bad_tb || many;
