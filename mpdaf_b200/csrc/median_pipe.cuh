@@ -282,4 +282,163 @@ median_pipe_kernel(const ClipArgs A, const long long ntiles, const __grid_consta
     }
 }
 
+// ---- 49 .. 128 exposures: the stack of a voxel pair split between two lanes (as in sigclip_duo.cuh) ------------------------
+// A tile is 32 voxels; lanes l and l + 16 share the voxel pair (2 (l & 15), 2 (l & 15) + 1) and each takes HB of the 2 HB
+// exposure slots for BOTH voxels into registers (invalid samples become +inf: they sort to the top), sorts its two
+// HB-deep stacks with the float32 network and stores them as sorted columns.  The lower lane then finds the two middle
+// values of voxel 0 in the union of the two lanes' columns by elimination (sigclip_runs.cuh), the upper lane those of
+// voxel 1.  Two sorts of HB per voxel instead of one of 2 HB (734 against ~1000 comparators at 96 exposures), a TMA
+// pipeline instead of register gathers.  Bit-identical to the reference (tools.c:39-51).
+template <int HB>
+struct MedianDuoCfg {
+    static constexpr int NB = 2 * HB;
+    static constexpr int stage_bytes = NB * 32 * 4;
+    static constexpr int col_bytes = HB * 32 * 8;       // sorted float32 columns: (voxel 0, voxel 1) per lane and rank
+    static constexpr int c_regs = 2048 / (2 * HB + 48);
+    static constexpr int c_smem = (220 * 1024) / (stage_bytes + col_bytes);
+    static constexpr int c_min = c_regs < c_smem ? c_regs : c_smem;
+    static constexpr int c_cap = c_min < 16 ? c_min : 16;
+    static constexpr int C = (c_cap > 4 && c_cap % 4 == 1) ? c_cap - 1 : c_cap;
+    static constexpr int threads = C * 32;
+    static_assert(C >= 2, "stack too deep for the two-lane median kernel");
+};
+
+template <int HB>
+struct MedianDuoSmem {
+    float stage[MedianDuoCfg<HB>::C][2 * HB][32];
+    float2 col[MedianDuoCfg<HB>::C][HB][32];
+    unsigned long long full[MedianDuoCfg<HB>::C];
+};
+
+template <int HB>
+__global__ void __launch_bounds__(MedianDuoCfg<HB>::threads, 1)
+median_duo_kernel(const ClipArgs A, const long long ntiles, const __grid_constant__ TmaMaps M)
+{
+    using Cfg = MedianDuoCfg<HB>;
+    constexpr int NB = 2 * HB, C = Cfg::C;
+    constexpr int W = ExpSet<HB>::W;
+    constexpr unsigned FULLM = 0xffffffffu;
+    constexpr unsigned kTileBytes = NB * 32 * sizeof(float);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    MedianDuoSmem<HB>& sm = *reinterpret_cast<MedianDuoSmem<HB>*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, c = tid >> 5;
+    const int half = lane >> 4, pr = lane & 15, e_base = half * HB;
+    if (tid == 0) {
+        for (int s = 0; s < C; s++) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const unsigned one = (unsigned)(A.nfiles > 0);
+    const unsigned minus_one = 0u - one;
+    TransposeConsts tc;
+    tc.init(lane);
+    unsigned cnt[2][W];
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+#pragma unroll
+        for (int k = 0; k < W; k++) cnt[g][k] = 0u;
+    }
+    unsigned tiles_done = 0;
+    auto request_tile = [&](long long j) {             // lane 0 only: this warp's j-th tile into its stage
+        const long long t = (long long)blockIdx.x + (j * C + c) * (long long)gridDim.x;
+        if (t >= ntiles) return;
+        mbar_expect_tx(&sm.full[c], kTileBytes);
+        tma_load_2d(&sm.stage[c][0][0], &M.data, (int)(t << 5), 0, &sm.full[c]);
+    };
+    if (lane == 0) request_tile(0);
+    const float* colf_own = reinterpret_cast<const float*>(&sm.col[c][0][lane]) + half;        // rank q of my voxel: [q * 64]
+    const float* colf_par = reinterpret_cast<const float*>(&sm.col[c][0][lane ^ 16]) + half;
+    long long tile = (long long)blockIdx.x + (long long)c * gridDim.x;
+    for (long long j = 0; tile < ntiles; j++, tile += (long long)C * gridDim.x) {
+        const float (*dt)[32] = sm.stage[c];
+        mbar_wait(&sm.full[c], (unsigned)j & 1u);
+        const long long v0 = (tile << 5) + 2 * pr;
+        float key[2][HB];
+#pragma unroll
+        for (int i = 0; i < HB; i++) {
+            const float2 dd = *reinterpret_cast<const float2*>(&dt[e_base + i][2 * pr]);
+            key[0][i] = dd.x;
+            key[1][i] = dd.y;
+        }
+        __syncwarp();
+        if (lane == 0) request_tile(j + 1);            // the samples are in registers: the stage is refilled at once
+        int n_own[2];
+        ExpSet<HB> inval[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int i = 0; i < HB; i++) {
+                const float d = key[h][i];
+                const bool ok = (d == d);              // slots beyond nfiles and voxels beyond nvox arrive as NaN (TMA fill)
+                key[h][i] = ok ? d : CUDART_INF_F;
+                if (!ok) inval[h].set(i);
+            }
+            n_own[h] = HB - inval[h].count();
+            sort_keys_mixed<HB, 1>(key[h], one, minus_one);
+        }
+#pragma unroll
+        for (int q = 0; q < HB; q++) sm.col[c][q][lane] = make_float2(key[0][q], key[1][q]);
+        __syncwarp();
+        // my voxel: `half`; its valid samples are the first nA ranks of my column and the first nB of the partner's
+        const int nA = half ? n_own[1] : n_own[0];
+        const int nB = __shfl_xor_sync(FULLM, half ? n_own[0] : n_own[1], 16);
+        const int n = nA + nB;
+        double med = CUDART_NAN;
+        if (n > 0) {
+            int pa = 0, pb = 0;
+            int need = (n - 1) >> 1;                   // ranks below the lower middle
+            while (need > 0) {
+                const int t = (need + 1) >> 1;
+                const bool ia = pa + t - 1 < nA, ib = pb + t - 1 < nB;
+                const float xa = ia ? colf_own[(pa + t - 1) * 64] : 0.f;
+                const float xb = ib ? colf_par[(pb + t - 1) * 64] : 0.f;
+                if (ia && (!ib || xa <= xb)) pa += t; else pb += t;     // (a valid sample may itself be +inf)
+                need -= t;
+            }
+            bool ia = pa < nA, ib = pb < nB;
+            float xa = ia ? colf_own[pa * 64] : 0.f, xb = ib ? colf_par[pb * 64] : 0.f;
+            const bool takeA = ia && (!ib || xa <= xb);
+            const float lo = takeA ? xa : xb;
+            float hi = lo;
+            if (!(n & 1)) {
+                if (takeA) { pa++; ia = pa < nA; xa = ia ? colf_own[pa * 64] : 0.f; }
+                else { pb++; ib = pb < nB; xb = ib ? colf_par[pb * 64] : 0.f; }
+                hi = (ia && (!ib || xa <= xb)) ? xa : xb;
+            }
+            med = (n & 1) ? (double)lo : ((double)lo + (double)hi) * 0.5;          // tools.c:45-48
+        }
+        const double med_o = __shfl_xor_sync(FULLM, med, 16);
+        const int n_o = __shfl_xor_sync(FULLM, n, 16);
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+#pragma unroll
+                for (int kk = 0; kk < W; kk++) cnt[g][kk] += __popc(tc.apply(half == g ? inval[h].w[kk] : 0u));
+            }
+        }
+        tiles_done++;
+        if (half == 0) {                               // the lower lane holds voxel 0's result and receives voxel 1's
+            if (v0 + 1 < A.nvox) {
+                *reinterpret_cast<double2*>(A.out + v0) = make_double2(med, med_o);
+                *reinterpret_cast<int2*>(A.expmap + v0) = make_int2(n, n_o);
+            } else if (v0 < A.nvox) {
+                A.out[v0] = med;
+                A.expmap[v0] = n;
+            }
+        }
+        __syncwarp();                                  // the columns are rewritten by the next tile
+    }
+    const unsigned seen = tiles_done * 32u;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+#pragma unroll
+        for (int kk = 0; kk < W; kk++) {
+            const int e = g * HB + 32 * kk + lane;
+            if (32 * kk + lane < HB && e < A.nfiles) atomicAdd(A.valid_cnt + e, (unsigned long long)(seen - cnt[g][kk]));
+        }
+    }
+}
+
 }  // namespace mb

@@ -342,6 +342,35 @@ int launch_median_warp_impl(const Job& j, LaunchCtx& ctx)
             return MPDAF_B200_OK;
         }
     }
+    // 49 .. 96 exposures on pitched rows: the two-lane form (median_pipe.cuh, median_duo_kernel): 4275 / 2843 GB/s at N = 64 / 96
+    // against 3264 / 2406 of the register-gather kernel, which stays ahead at 128 (2122 against 1931: six warps per SM there)
+    if constexpr (NB == 64 || NB == 96) {
+        constexpr int HB = NB / 2;
+        const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr || std::getenv("MPDAF_B200_NO_DUO") != nullptr;
+        unsigned long long dp = 0ull;
+        if (!off && j.nfiles > HB && j.data != nullptr && !(reinterpret_cast<uintptr_t>(j.data[0]) & 15u)) {
+            const long long step = static_cast<const char*>(j.data[1]) - static_cast<const char*>(j.data[0]);
+            bool ok = step >= j.a.nvox * 4 && (step & 15) == 0;
+            for (int i = 2; ok && i < j.nfiles; i++) ok = static_cast<const char*>(j.data[i]) - static_cast<const char*>(j.data[i - 1]) == step;
+            if (ok) dp = (unsigned long long)(step >> 2);
+        }
+        TmaMaps maps;
+        std::memset(&maps, 0, sizeof(maps));
+        if (dp != 0 && j.a.nvox >= 1 && j.a.nvox < 0x7FFFFF00LL && !(reinterpret_cast<uintptr_t>(j.a.out) & 15u) &&
+            !(reinterpret_cast<uintptr_t>(j.a.expmap) & 7u) &&
+            encode_stack_map(maps.data, j.data[0], (unsigned long long)j.a.nvox, j.nfiles, 4ull * dp, 32u, NB, true)) {
+            using Cfg = MedianDuoCfg<HB>;
+            std::snprintf(ctx.name, ctx.name_len, "median_duo<%d>", NB);
+            const int smem = (int)sizeof(MedianDuoSmem<HB>);
+            MB_CUDA(cudaFuncSetAttribute(median_duo_kernel<HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            const long long ntiles = (j.a.nvox + 31) / 32;
+            const int grid = (int)std::max(1LL, std::min(ntiles, (long long)ctx.sm_count));
+            median_duo_kernel<HB><<<grid, Cfg::threads, smem, ctx.stream>>>(j.a, ntiles, maps);
+            MB_CUDA(cudaGetLastError());
+            ctx.launches++;
+            return MPDAF_B200_OK;
+        }
+    }
     TileArgs<NB> s;
     fill_tile_args(s, j);
     const bool full = (j.nfiles == NB);

@@ -185,6 +185,12 @@ def test_duo_kernel_65_to_128_exposures(n):
     data[70 % n][0, 1, :6] = -np.inf
     want = oracle.combine_port(data, var, nclip=2.0)
     assert_same_result(cuda().combine_cuda(data, var, nclip=2.0, location="device_pitched"), want)
+    # the median of the same stacks: two sorted half-stacks per voxel, the middle of their union (median_duo_kernel)
+    data[5][1, :, :] = np.nan
+    wm = oracle.median_port(data)
+    gm = cuda().median_cuda(data, location="host")
+    assert ("median_duo<" in cuda().kernel_name()) == (n <= 96), cuda().kernel_name()
+    assert_same_result(gm, wm, median=True)
 
 
 @pytest.mark.parametrize("n", [129, 192, 256, 257, 400, 500])
@@ -824,3 +830,18 @@ def test_slow_queue_overflow_is_recomputed_in_place(monkeypatch):
         assert "sigclip_pair<24" in cuda().kernel_name()
         assert_same_result(got, want)
         assert cuda().slow_voxels() > 100
+    # the same routes of the two-lane kernel (65 .. 128 exposures): queue, and in-place recomputation when it is full
+    for n in (96, 128):
+        data, var = random_stack(rng, n, (3, 9, 17), nan_frac=0.1, outlier_frac=0.05, ties=True)
+        kw = dict(scales=np.linspace(0.9, 1.1, n), offsets=np.linspace(-0.1, 0.1, n), nclip=1.5, nmax=5)
+        want = oracle.combine_port(data, var, **kw)
+        for cap in ("3", "0", None):
+            if cap is None:
+                monkeypatch.delenv("MPDAF_B200_SLOW_CAP", raising=False)
+            else:
+                monkeypatch.setenv("MPDAF_B200_SLOW_CAP", cap)
+            cuda().slow_voxels()
+            got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
+            assert "sigclip_duo<" in cuda().kernel_name()
+            assert_same_result(got, want)
+            assert cuda().slow_voxels() > 20
