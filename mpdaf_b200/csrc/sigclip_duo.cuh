@@ -57,7 +57,7 @@ static_assert(sizeof(DuoSmem<48>) <= 227 * 1024 && sizeof(DuoSmem<64>) <= 227 * 
 
 // (queued voxels: sigclip_pair_slow_kernel<2 * HB, UNIT>, the warp-per-voxel restatement, handles up to 128 samples)
 
-template <int HB, bool UNIT, bool PROP>
+template <int HB, bool UNIT, bool PROP, bool MAD = false>
 __global__ void __launch_bounds__(DuoCfg<HB>::threads, 1)
 sigclip_duo_kernel(const PairArgs<2 * HB> S, const ClipArgs A, const long long ntiles, unsigned* __restrict__ slow_q,
                    unsigned* __restrict__ slow_n, const unsigned slow_cap, const int flags, const __grid_constant__ TmaMaps M)
@@ -285,7 +285,8 @@ sigclip_duo_kernel(const PairArgs<2 * HB> S, const ClipArgs A, const long long n
                 const double rm = sm.rcp[m];
                 const double dm1 = T1m * rm;
                 var_k = __fma_rn(S2m, rm, -(dm1 * dm1));
-                const bool bad = !(var_k >= 0x1p-13 * (S20m * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100);
+                // (MAD: the moments only give the mean; sigma comes from the keys, its uncertainty is part of Tb below)
+                const bool bad = !MAD && (!(var_k >= 0x1p-13 * (S20m * rm)) || !(var_k < 0x1p100) || !(var_k > 0x1p-100));
                 // the two middle keys of the union of the two windows, by elimination (sigclip_runs.cuh)
                 int pa = ao, pb = ap;
                 int need = (m - 1) >> 1;                             // ranks below the lower middle
@@ -300,6 +301,8 @@ sigclip_duo_kernel(const PairArgs<2 * HB> S, const ClipArgs A, const long long n
                 float hb = pb < bp ? fkey(cB[pb * 64]) : CUDART_INF_F;
                 const float kl = fminf(ha, hb);
                 float kh = kl;
+                // (MAD) the lower middle and everything below it: ranks up to la in my column, up to lb in the partner's
+                const int la0 = (ha <= hb) ? pa : pa - 1, lb0 = (ha <= hb) ? pb - 1 : pb;
                 if (!(m & 1)) {
                     if (ha <= hb) { pa++; ha = pa < bo ? fkey(cA[pa * 64]) : CUDART_INF_F; }
                     else { pb++; hb = pb < bp ? fkey(cB[pb * 64]) : CUDART_INF_F; }
@@ -307,12 +310,45 @@ sigclip_duo_kernel(const PairArgs<2 * HB> S, const ClipArgs A, const long long n
                 }
                 const float km = 0.5f * (kh + kl);
                 const float emed = krel32 * fmaxf(fabsf(kh), fabsf(kl)) + e0m;
-                float sg;
-                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(__double2float_rn(var_k)));
+                float sg, esg = 0.f;
+                if constexpr (MAD) {
+                    // sigma = 1.4826 * median(|w - median|) (tools.c:67-74) on the keys: the absolute deviations form four
+                    // sorted runs (below / above the median in either column), merged outward from the median; the error
+                    // model is the pair kernel's (sigclip_pair.cuh)
+                    int la = la0, lb = lb0, ra = la0 + 1, rb = lb0 + 1;
+                    float dla = la >= ao ? km - fkey(cA[la * 64]) : CUDART_INF_F;
+                    float dlb = lb >= ap ? km - fkey(cB[lb * 64]) : CUDART_INF_F;
+                    float dra = ra < bo ? fkey(cA[ra * 64]) - km : CUDART_INF_F;
+                    float drb = rb < bp ? fkey(cB[rb * 64]) - km : CUDART_INF_F;
+                    float cur = 0.f, prev = 0.f;
+                    for (int s2 = 0; s2 <= (m >> 1); s2++) {
+                        prev = cur;
+                        if (dla <= dlb && dla <= dra && dla <= drb) {
+                            cur = dla; la--;
+                            dla = la >= ao ? km - fkey(cA[la * 64]) : CUDART_INF_F;
+                        } else if (dlb <= dra && dlb <= drb) {
+                            cur = dlb; lb--;
+                            dlb = lb >= ap ? km - fkey(cB[lb * 64]) : CUDART_INF_F;
+                        } else if (dra <= drb) {
+                            cur = dra; ra++;
+                            dra = ra < bo ? fkey(cA[ra * 64]) - km : CUDART_INF_F;
+                        } else {
+                            cur = drb; rb++;
+                            drb = rb < bp ? fkey(cB[rb * 64]) - km : CUDART_INF_F;
+                        }
+                    }
+                    cur = fabsf(cur);
+                    prev = fabsf(prev);
+                    const float madk = (m & 1) ? cur : 0.5f * (cur + prev);
+                    sg = madk * 1.4826f;
+                    esg = 1.4826f * (krel32 * 1.02f * (fabsf(km) + madk) + e0m + emed) + 0x1p-20f * sg;
+                } else {
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(__double2float_rn(var_k)));
+                }
                 const float lo_s = nlo32 * sg, up_s = nup32 * sg;
                 clo = km - lo_s;
                 cup = km + up_s;
-                Tb = emed + 0x1p-19f * (fabsf(km) + lo_s + up_s);
+                Tb = emed + fmaxf(nlo32, nup32) * esg + 0x1p-19f * (fabsf(km) + lo_s + up_s);
                 const bool bad_tb = !(Tb < 0x1p100f);
                 const float yl = clo + Tb + e0m, xu = cup - Tb - e0m;
                 const float kL2 = yl * (yl >= 0.f ? c2f : c1f);

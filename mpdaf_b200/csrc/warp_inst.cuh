@@ -167,7 +167,7 @@ int launch_pair_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
 }
 
 // Pair kernel with the stack split between two lanes (sigclip_duo.cuh): float32 stacks of 65 .. 128 exposures on equally
-// pitched, 16-byte aligned rows, no MAD.
+// pitched, 16-byte aligned rows (MAD with var = 'propagate' only).
 template <int NB>
 int launch_duo_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
 {
@@ -178,7 +178,8 @@ int launch_duo_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
         constexpr int HB = NB / 2;
         const bool off = std::getenv("MPDAF_B200_NO_PAIR") != nullptr || std::getenv("MPDAF_B200_NO_DUO") != nullptr;
         const bool need_var = j.a.typ_var == 0;
-        if (off || j.median || j.a.mad || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL || j.nfiles <= HB) return MPDAF_B200_OK;
+        if (off || j.median || ctx.slow_q == nullptr || j.a.nvox < 1 || j.a.nvox >= 0x7FFFFF00LL || j.nfiles <= HB) return MPDAF_B200_OK;
+        if (j.a.mad && !need_var) return MPDAF_B200_OK;      // MAD: with var = 'propagate' only (as in the pair kernel)
         auto pitch_of = [&](const void* const* rows) -> unsigned long long {
             if (rows == nullptr || (reinterpret_cast<uintptr_t>(rows[0]) & 15u)) return 0ull;
             const long long step = static_cast<const char*>(rows[1]) - static_cast<const char*>(rows[0]);
@@ -233,6 +234,11 @@ int launch_duo_impl(const Job& j, bool unit, LaunchCtx& ctx, bool& taken)
             return MPDAF_B200_OK;
         };
         taken = true;
+        if (j.a.mad) {
+            std::snprintf(ctx.name, ctx.name_len, "sigclip_duo<%d,%s,mad>", NB, unit ? "unit" : "scaled");
+            if (unit) return launch(sigclip_duo_kernel<HB, true, true, true>, sigclip_pair_slow_kernel<NB, true>);
+            return launch(sigclip_duo_kernel<HB, false, true, true>, sigclip_pair_slow_kernel<NB, false>);
+        }
         if (unit) return need_var ? launch(sigclip_duo_kernel<HB, true, true>, sigclip_pair_slow_kernel<NB, true>)
                                   : launch(sigclip_duo_kernel<HB, true, false>, sigclip_pair_slow_kernel<NB, true>);
         return need_var ? launch(sigclip_duo_kernel<HB, false, true>, sigclip_pair_slow_kernel<NB, false>)

@@ -180,6 +180,12 @@ def test_duo_kernel_65_to_128_exposures(n):
                 got = cuda().combine_cuda(data, var, location=location, **kw)
                 assert "sigclip_duo<" in cuda().kernel_name(), cuda().kernel_name()
                 assert_same_result(got, want)
+        # MAD with var = 'propagate': sigma from the four sorted runs of absolute key deviations of the two columns
+        for kw in (dict(nclip=3.0, mad=True), dict(scales=scales, offsets=offsets, nclip=(2.0, 2.5), nmax=4, mad=True)):
+            want = oracle.combine_port(data, var, **kw)
+            got = cuda().combine_cuda(data, var, location="device_pitched", **kw)
+            assert "sigclip_duo<" in cuda().kernel_name() and "mad" in cuda().kernel_name(), cuda().kernel_name()
+            assert_same_result(got, want)
     # non-finite samples and a tiny queue (voxels recomputed in place)
     data[3][0, 0, :6] = np.inf
     data[70 % n][0, 1, :6] = -np.inf
