@@ -561,13 +561,14 @@ sigclip_duo_kernel(const PairArgs<2 * HB> S, const ClipArgs A, const long long n
             unsigned neg = 0u;
             if (pair_ok) {
                 // this lane's rows: slots e_base .. e_base + HB - 1; slots beyond the stack re-read its last row (dropped anyway)
-                const int first = e_base < A.nfiles ? e_base : A.nfiles - 1;
-                const float* vp = static_cast<const float*>(S.var0) + (size_t)first * S.vstride + v0;
+                const int last = A.nfiles - 1;
+                const float* vp = static_cast<const float*>(S.var0) + v0;
                 float2 sv[HB];
 #pragma unroll
                 for (int i = 0; i < HB; i++) {
-                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
-                    if (e_base + i + 1 < A.nfiles) vp += S.vstride;
+                    const int e = e_base + i;
+                    const float* rp = vp + (size_t)(e < last ? e : last) * S.vstride;      // row min(slot, nfiles - 1): never beyond the stack
+                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(rp));
                 }
                 asm volatile("" ::: "memory");
                 count_tile();

@@ -865,20 +865,13 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             } else if (pair_ok) {
                 const float* vp = static_cast<const float*>(S.var0) + v0;
                 float2 sv[NB];
-                if (A.nfiles == NB) {
+                // (slots beyond a stack that does not fill its bucket re-read the last row: their samples are invalid -- NaN-filled
+                // by the tensor map -- hence dropped; a row beyond the stack is never addressed)
+                const int last = A.nfiles - 1;
 #pragma unroll
-                    for (int i = 0; i < NB; i++) {
-                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
-                        vp += S.vstride;
-                    }
-                } else {
-                    // fewer exposures than slots: the slots beyond the stack re-read its last row (their samples are
-                    // invalid -- NaN-filled by the tensor map -- hence dropped); a row beyond the stack is never addressed
-#pragma unroll
-                    for (int i = 0; i < NB; i++) {
-                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
-                        if (i + 1 < A.nfiles) vp += S.vstride;
-                    }
+                for (int i = 0; i < NB; i++) {
+                    const float* rp = vp + (size_t)(i < last ? i : last) * S.vstride;       // row min(i, nfiles - 1): no dependent chain
+                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(rp));
                 }
                 asm volatile("" ::: "memory");
                 count_tile();                     // the counter transposes run while the STAT rows are on their way
