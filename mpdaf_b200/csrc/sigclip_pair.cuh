@@ -865,13 +865,29 @@ sigclip_pair_kernel(const PairArgs<NB> S, const ClipArgs A, const long long ntil
             } else if (pair_ok) {
                 const float* vp = static_cast<const float*>(S.var0) + v0;
                 float2 sv[NB];
-                // (slots beyond a stack that does not fill its bucket re-read the last row: their samples are invalid -- NaN-filled
-                // by the tensor map -- hence dropped; a row beyond the stack is never addressed)
-                const int last = A.nfiles - 1;
+                // Slots beyond a stack that does not fill its bucket must not be addressed (their samples are invalid -- NaN-filled
+                // by the tensor map -- hence dropped): they re-read the stack's last row.  Two forms, chosen by measurement: a
+                // pointer chain with a separate clamped copy for partial buckets (fastest without MAD), and row = min(slot,
+                // nfiles - 1) computed per load (the chain form costs the larger MAD kernels 25 .. 40 %: N = 48, 4.29 against 3.09 ms)
+                if constexpr (MAD) {
+                    const int last = A.nfiles - 1;
 #pragma unroll
-                for (int i = 0; i < NB; i++) {
-                    const float* rp = vp + (size_t)(i < last ? i : last) * S.vstride;       // row min(i, nfiles - 1): no dependent chain
-                    asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(rp));
+                    for (int i = 0; i < NB; i++) {
+                        const float* rp = vp + (size_t)(i < last ? i : last) * S.vstride;
+                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(rp));
+                    }
+                } else if (A.nfiles == NB) {
+#pragma unroll
+                    for (int i = 0; i < NB; i++) {
+                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
+                        vp += S.vstride;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NB; i++) {
+                        asm volatile("ld.global.cs.v2.f32 {%0, %1}, [%2];" : "=f"(sv[i].x), "=f"(sv[i].y) : "l"(vp));
+                        if (i + 1 < A.nfiles) vp += S.vstride;
+                    }
                 }
                 asm volatile("" ::: "memory");
                 count_tile();                     // the counter transposes run while the STAT rows are on their way
